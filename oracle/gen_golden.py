@@ -1,0 +1,112 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference (oracle/ref_harness.py) in the build
+container.  Run:  python oracle/gen_golden.py [--full]      (test infrastructure, not product code)
+
+Fixtures:
+  toy_step.npz       toy 3D-MAE (E=64/2 heads, D=32/1 head, 12x64x64, B=2): weights, volume, noise,
+                     reference loss / frame_losses / mask / pred / every parameter gradient (fp32 CPU).
+  toy_step_normpix.npz   same with norm_pix_loss=True (loss + a few grads only)
+  masking_cases.npz  reference random_masking on noise rows at L in {1024,4096,5120}: natural torch.rand
+                     noise and 1/37-quantised noise (ties; argsort forced stable = CUDA radix-sort behaviour,
+                     SURVEY H1) and tie-free noise (reference argsort untouched).
+  full_cfg1.json     ViT-L, 1x48x256x256, mask 0.9 (BASELINE cfg-1): reference loss / mask sum / pred stats
+                     for oracle.init_state_dict(seed 0) weights (only with --full; ~1 min).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import mae3d_oracle as O  # noqa: E402
+from oracle import ref_harness as R  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TOY = O.MAEConfig(input_size=64, patch_size=16, in_chans=1, embed_dim=64, depth=2, num_heads=2,
+                  decoder_embed_dim=32, decoder_depth=1, decoder_num_heads=1, num_frames=12, t_patch_size=3,
+                  pred_t_dim=12, high_res_input_size=128)
+
+
+def toy_inputs():
+    sd = O.perturb_state_dict(O.init_state_dict(TOY, seed=0))
+    vol = O.synthetic_volume(2, 12, 64, 64, seed=0, zero_pad_frames=1)
+    noise = O.synthetic_noise(2, TOY.t_grid * TOY.grid ** 2, seed=1)
+    return sd, vol, noise
+
+
+def gen_toy(norm_pix):
+    cfg = O.MAEConfig(**{**TOY.__dict__, "norm_pix_loss": norm_pix})
+    sd, vol, noise = toy_inputs()
+    m = R.build_reference(**cfg.ref_kwargs())
+    missing = m.load_state_dict(sd, strict=True)
+    out = R.run_reference(m, vol, noise, 0.9, frame_loss=True, force_stable_argsort=True, backward=True)
+    rec = {"loss": out["loss"].detach().numpy(), "frame_losses": out["frame_losses"].detach().numpy(),
+           "mask": out["mask"].numpy(), "volume": vol.numpy(), "noise": noise.numpy()}
+    if not norm_pix:
+        rec["pred"] = out["pred"].detach().numpy()
+        for k, v in sd.items():
+            rec["w::" + k] = v.numpy()
+        for k, v in out["grads"].items():
+            rec["g::" + k] = v.numpy()
+    else:
+        for k in ("decoder_pred.weight", "blocks.0.mixer.Wqkv.weight", "pos_embed_spatial", "mask_token"):
+            rec["g::" + k] = out["grads"][k].numpy()
+    name = "toy_step_normpix.npz" if norm_pix else "toy_step.npz"
+    np.savez_compressed(os.path.join(GOLD, name), **rec)
+    print(name, "loss", float(out["loss"]), "mask sum", float(out["mask"].sum()))
+
+
+def gen_masking():
+    m = R.build_reference(**TOY.ref_kwargs())
+    rec = {}
+    for L in (1024, 4096, 5120):
+        for kind in ("natural", "tiefree", "quantized"):
+            noise = O.synthetic_noise(2, L, seed=7 + L, tie_free=(kind == "tiefree"))
+            if kind == "quantized":  # many exact ties, some straddling the keep boundary
+                noise = torch.floor(noise * 37.0) / 37.0
+            x = torch.arange(2 * L * 2, dtype=torch.float32).view(2, L, 2)
+            with R.inject_noise(noise, force_stable_argsort=(kind != "tiefree")):
+                xm, mask, ids_restore, ids_keep = m.random_masking(x, 0.9)
+            rec[f"{kind}_{L}_noise"] = noise.numpy()
+            rec[f"{kind}_{L}_mask"] = mask.numpy().astype(np.uint8)
+            rec[f"{kind}_{L}_ids_restore"] = ids_restore.numpy().astype(np.int32)
+            rec[f"{kind}_{L}_ids_keep"] = ids_keep.numpy().astype(np.int32)
+            print(kind, L, "keep", ids_keep.shape[1],
+                  "rows with ties", int(sum(len(torch.unique(r)) < L for r in noise)))
+    np.savez_compressed(os.path.join(GOLD, "masking_cases.npz"), **rec)
+
+
+def gen_full():
+    cfg = O.MAEConfig(num_frames=48, pred_t_dim=48)
+    sd = O.init_state_dict(cfg, seed=0)
+    vol = O.synthetic_volume(1, 48, 256, 256, seed=0)
+    noise = O.synthetic_noise(1, cfg.t_grid * cfg.grid ** 2, seed=1)
+    m = R.build_reference(**cfg.ref_kwargs())
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = R.run_reference(m, vol, noise, 0.9, frame_loss=True, force_stable_argsort=True)
+    rec = {"config": "ViT-L 1x48x256x256 mask 0.9 fp32 CPU, oracle.init_state_dict(seed=0), volume seed 0, noise seed 1",
+           "loss": float(out["loss"]), "mask_sum": float(out["mask"].sum()),
+           "frame_losses": out["frame_losses"].flatten().tolist(),
+           "pred_mean": float(out["pred"].mean()), "pred_std": float(out["pred"].std()),
+           "pred_first8": out["pred"].flatten()[:8].tolist(),
+           "n_params": sum(v.numel() for v in sd.values())}
+    json.dump(rec, open(os.path.join(GOLD, "full_cfg1.json"), "w"), indent=1)
+    print(rec)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    gen_toy(False)
+    gen_toy(True)
+    gen_masking()
+    if a.full:
+        gen_full()

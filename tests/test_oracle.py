@@ -1,0 +1,156 @@
+"""CPU tests of the oracle: against the committed reference-generated fixtures, and (where the reference
+tree is present, i.e. in the build container) against the unmodified reference itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mae3d_oracle as O
+from oracle import ref_harness as R
+from oracle.gen_golden import TOY, toy_inputs
+
+needs_ref = pytest.mark.skipif(not R.reference_available(), reason="/root/reference not present")
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_len_keep_truncation():
+    # quirk Q2 (models_mae_joint_res_flash_attn.py:349)
+    assert O.len_keep_of(5120, 0.9) == 511
+    assert O.len_keep_of(4096, 0.9) == 409
+    assert O.len_keep_of(1024, 0.75) == 256
+    assert O.len_keep_of(1024, 0.85) == 153
+
+
+def test_patchify_roundtrip_and_gemm_view():
+    x = torch.randn(2, 1, 12, 64, 64)
+    p = O.patchify(x, 16, 3)
+    assert p.shape == (2, 4 * 16, 768)
+    assert torch.equal(O.unpatchify(p, 2, 1, 12, 64, 64, 16, 3), x)
+    # patchify(imgs) is exactly the A matrix of the patch-embed GEMM for C=1
+    w, b = torch.randn(32, 1, 3, 16, 16), torch.randn(32)
+    y = O.patch_embed(x, w, b).reshape(2, 64, 32)
+    assert torch.allclose(y, p @ w.view(32, -1).t() + b, atol=1e-4, rtol=1e-4)
+
+
+def test_masking_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "masking_cases.npz"))
+    for L in (1024, 4096, 5120):
+        for kind in ("natural", "tiefree", "quantized"):
+            noise = torch.from_numpy(g[f"{kind}_{L}_noise"])
+            x = torch.arange(2 * L * 2, dtype=torch.float32).view(2, L, 2)
+            xm, mask, ids_restore, ids_keep = O.random_masking(x, 0.9, noise)
+            assert np.array_equal(ids_restore.numpy(), g[f"{kind}_{L}_ids_restore"].astype(np.int64)), (kind, L)
+            assert np.array_equal(ids_keep.numpy(), g[f"{kind}_{L}_ids_keep"].astype(np.int64))
+            assert np.array_equal(mask.numpy().astype(np.uint8), g[f"{kind}_{L}_mask"])
+            # equivalences the CUDA path relies on (SURVEY §8a random_masking row)
+            keep = ids_keep.shape[1]
+            assert torch.equal(mask, (ids_restore >= keep).float())
+            assert torch.equal(xm, torch.gather(x, 1, ids_keep[..., None].expand(-1, -1, 2)))
+
+
+@pytest.mark.parametrize("norm_pix", [False, True])
+def test_toy_step_golden(golden_dir, norm_pix):
+    g = np.load(os.path.join(golden_dir, "toy_step_normpix.npz" if norm_pix else "toy_step.npz"))
+    cfg = O.MAEConfig(**{**TOY.__dict__, "norm_pix_loss": norm_pix})
+    sd, vol, noise = toy_inputs()
+    assert np.array_equal(vol.numpy(), g["volume"]) and np.array_equal(noise.numpy(), g["noise"])
+    (out, grads) = O.forward_backward(cfg, sd, vol, 0.9, noise, frame_loss=True)
+    (loss, fl), pred, mask = out
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert np.array_equal(mask.numpy(), g["mask"])
+    assert _rel(fl.detach(), g["frame_losses"]) < 1e-6
+    if not norm_pix:
+        assert _rel(pred.detach(), g["pred"]) < 1e-6
+    n = 0
+    for k in g.files:
+        if k.startswith("g::"):
+            assert _rel(grads[k[3:]], g[k]) < 2e-5, k
+            n += 1
+    assert n >= 4
+    if not norm_pix:
+        # the two high-res patch-embed tensors get no gradient on a 3D-only step (quirk Q13)
+        assert set(sd) - set(grads) == {"high_res_patch_embed.proj.weight", "high_res_patch_embed.proj.bias"}
+
+
+@needs_ref
+def test_oracle_vs_reference_tiefree_unpatched_argsort():
+    """The unmodified reference (its own torch.argsort) on tie-free noise == oracle, fwd + bwd."""
+    sd, vol, _ = toy_inputs()
+    noise = O.synthetic_noise(2, 64, seed=5, tie_free=True)
+    m = R.build_reference(**TOY.ref_kwargs())
+    m.load_state_dict(sd, strict=True)
+    ref = R.run_reference(m, vol, noise, 0.9, frame_loss=True, backward=True)
+    (out, grads) = O.forward_backward(TOY, sd, vol, 0.9, noise, frame_loss=True)
+    (loss, fl), pred, mask = out
+    assert torch.equal(mask, ref["mask"])
+    assert abs(float(loss) - float(ref["loss"])) < 1e-6
+    assert _rel(pred.detach(), ref["pred"].detach()) < 1e-6
+    assert set(grads) == set(ref["grads"])
+    for k in grads:
+        assert _rel(grads[k], ref["grads"][k]) < 2e-5, k
+
+
+@needs_ref
+def test_oracle_vs_reference_highres_2d_branch():
+    """cfg-4 shape family: [B,1,3,128,128] 'high-res' input -> T'=1 'none' temporal path, raw spatial table."""
+    sd, _, _ = toy_inputs()
+    vol = O.synthetic_volume(2, 3, 128, 128, seed=3, zero_pad_frames=0)
+    noise = O.synthetic_noise(2, 64, seed=6, tie_free=True)
+    m = R.build_reference(**TOY.ref_kwargs())
+    m.load_state_dict(sd, strict=True)
+    ref = R.run_reference(m, vol, noise, 0.75, backward=True)
+    (out, grads) = O.forward_backward(TOY, sd, vol, 0.75, noise)
+    loss, pred, mask = out
+    assert torch.equal(mask, ref["mask"])
+    assert abs(float(loss) - float(ref["loss"])) < 1e-6
+    assert set(grads) == set(ref["grads"])  # quirk Q13, 2D-512-only step
+    for k in grads:
+        assert _rel(grads[k], ref["grads"][k]) < 2e-5, k
+
+
+@needs_ref
+def test_cpu_baseline_restatement_vs_reference_nonflash():
+    """oracle.cpu_baseline_forward == reference class with use_flash_attn=False (after key surgery)."""
+    sd, vol, _ = toy_inputs()
+    noise = O.synthetic_noise(2, 64, seed=5, tie_free=True)
+    m = R.build_reference(flash_semantics=False, **TOY.ref_kwargs())
+    ref_sd = {}
+    for k, v in sd.items():
+        if ".mixer.Wqkv." in k:
+            for i, n in enumerate("qkv"):
+                ref_sd[k.replace("mixer.Wqkv", f"attn.{n}")] = v.chunk(3, 0)[i]
+        elif ".mixer.out_proj." in k:
+            ref_sd[k.replace("mixer.out_proj", "attn.proj")] = v
+        else:
+            ref_sd[k] = v
+    m.load_state_dict(ref_sd, strict=True)
+    with torch.no_grad():
+        ref = R.run_reference(m, vol, noise, 0.9)
+        loss, pred, mask = O.cpu_baseline_forward(TOY, sd, vol, 0.9, noise)
+    assert torch.equal(mask, ref["mask"])
+    assert abs(float(loss) - float(ref["loss"])) < 1e-6
+    assert _rel(pred, ref["pred"]) < 1e-6
+
+
+@pytest.mark.slow
+def test_full_cfg1_golden(golden_dir):
+    """BASELINE cfg-1 (ViT-L, 1x48x256x256, mask 0.9, fp32 CPU): oracle reproduces the reference's loss."""
+    g = json.load(open(os.path.join(golden_dir, "full_cfg1.json")))
+    cfg = O.MAEConfig(num_frames=48, pred_t_dim=48)
+    sd = O.init_state_dict(cfg, seed=0)
+    assert sum(v.numel() for v in sd.values()) == g["n_params"] == 331626240
+    vol = O.synthetic_volume(1, 48, 256, 256, seed=0)
+    noise = O.synthetic_noise(1, 4096, seed=1)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        (loss, fl), pred, mask = O.forward(cfg, sd, vol, 0.9, noise, frame_loss=True)
+    assert float(mask.sum()) == g["mask_sum"] == 4096 - 409
+    assert abs(float(loss) - g["loss"]) < 2e-5 * g["loss"]
+    assert _rel(fl.flatten(), g["frame_losses"]) < 2e-5
+    assert _rel(pred.flatten()[:8], g["pred_first8"]) < 1e-4
