@@ -1,0 +1,164 @@
+/* octcube_b200 — C ABI of the B200 (sm_100a) kernels behind the OCTCube 3D-MAE pre-training step.
+ *
+ * The reference (ZucksLiu/OCTCubeM) has no FFI of its own: its operator surface is the Python nn.Module
+ * `MaskedAutoencoderViT` (Pre-training/models_mae_joint_res_flash_attn.py:29-790) whose arithmetic is delegated to
+ * ATen / cuDNN / cuBLASLt / the flash-attn pip package.  Every entry point below replaces one of those library
+ * call sites (cited per function; `models:` = Pre-training/models_mae_joint_res_flash_attn.py, `vv:` =
+ * Pre-training/custom_util/video_vit.py, `FA:` = flash_attn 2.8.3 python modules).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions:
+ *  - plain pointers + sizes; every pointer is a DEVICE pointer on the current device unless stated otherwise;
+ *  - the caller owns all memory (inputs, outputs, workspaces) and keeps it alive until `stream` passes the call;
+ *  - nothing here allocates, frees, synchronises the device or touches another stream;
+ *  - return 0 on success; <0 = argument/shape error (OCT_ERR_*), >0 = cudaError_t; message via oct_last_error();
+ *  - `stream` is a cudaStream_t passed as void*;
+ *  - dtype codes: OCT_F32 / OCT_BF16 for tensors that exist in both precisions; indices are int64 (bit-identical
+ *    to what torch.argsort hands the reference's callers); masks are float {0,1}.
+ */
+#ifndef OCTCUBE_B200_H
+#define OCTCUBE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* oct_stream_t;
+
+enum { OCT_OK = 0, OCT_ERR_INVALID = -1, OCT_ERR_UNSUPPORTED = -2, OCT_ERR_WORKSPACE = -3 };
+enum { OCT_F32 = 0, OCT_BF16 = 1, OCT_SIMT_BF16 = 2 /* attention only: CUDA-core math on bf16 tensors (validation aid) */ };
+
+/* GEMM operand layouts.  All matrices are row-major with explicit leading dimensions (in elements).
+ *   OCT_GEMM_NT : D[M,N] = A[M,K] · B[N,K]^T   (nn.Linear forward,  FA:mha.py:635,703  FA:mlp.py:48-50  models:511,595)
+ *   OCT_GEMM_NN : D[M,N] = A[M,K] · B[K,N]     (its dgrad:  dX = dY · W)
+ *   OCT_GEMM_TN : D[M,N] = A[K,M]^T · B[K,N]   (its wgrad:  dW = dY^T · X) */
+enum { OCT_GEMM_NT = 0, OCT_GEMM_NN = 1, OCT_GEMM_TN = 2 };
+
+/* GEMM epilogues (applied to the fp32 accumulator acc[m,n]):
+ *   OCT_EPI_NONE       D = acc (+ beta·D when beta==1, fp32 D only)
+ *   OCT_EPI_BIAS       D = acc + bias[n]
+ *   OCT_EPI_BIAS_GELU  aux = acc + bias[n] (pre-activation, same dtype as D);  D = gelu_erf(round(aux))
+ *   OCT_EPI_DGELU      D = acc · gelu_erf'(aux[m,n])          (fc2 dgrad fused with the GELU backward) */
+enum { OCT_EPI_NONE = 0, OCT_EPI_BIAS = 1, OCT_EPI_BIAS_GELU = 2, OCT_EPI_DGELU = 3 };
+
+/* compute paths: OCT_F32 = fp32 CUDA-core kernels (the 1e-4 parity mode);
+ *                OCT_BF16 = tcgen05 / TMEM / TMA tensor-core kernels (bf16 operands, fp32 accumulate). */
+
+const char* oct_version(void);
+const char* oct_last_error(void);
+/* sm_count / compute capability of the current device; returns OCT_ERR_UNSUPPORTED unless cc == 10.x */
+int oct_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- random_masking (models:336-372; replaces torch.rand-argsort-argsort-gather-ones-gather) ----------------
+ * Stable ascending sort of each noise row by (key, index) == torch.argsort on CUDA (radix sort).
+ * ids_restore[b, ids_shuffle[b,r]] = r ; ids_keep[b, r] = ids_shuffle[b, r] for r < keep ; mask = (ids_restore >= keep).
+ * noise [B,L] f32 (finite or +-inf, no NaN), ids_restore [B,L] i64, ids_keep [B,keep] i64, mask [B,L] f32. L <= 16384. */
+int oct_mask_sort(const float* noise, int64_t B, int64_t L, int64_t keep, int64_t* ids_restore, int64_t* ids_keep,
+                  float* mask, oct_stream_t stream);
+
+/* ---- patchify (models:289-314) and the kept-token variant --------------------------------------------------
+ * imgs [B,1,T,H,W] f32 -> out [B, L, u*p*p] (ids_keep == NULL) or out [B*keep, u*p*p] rows ids_keep[b,i];
+ * per-patch order (kt,kh,kw) == Conv3d weight order (vv:69-72), token order (t',h,w). out dtype f32|bf16.
+ * frame_idx (nullable, [T_sel] i64 on device): temporal index_select of models:630-640 (T_sel frames are used). */
+int oct_patchify(const float* imgs, void* out, int out_dtype, const int64_t* ids_keep, const int64_t* frame_idx,
+                 int64_t B, int64_t T, int64_t H, int64_t W, int64_t p, int64_t u, int64_t T_sel, int64_t keep,
+                 oct_stream_t stream);
+
+/* ---- PatchEmbed.forward (vv:74-83; replaces cuDNN Conv3d + permute copy) -----------------------------------
+ * im2col-free: the volume is addressed through a 5-D TMA box (kw,kh,w,h,frame), the contraction runs on tcgen05
+ * (kind::tf32, fp32 operands straight from HBM, fp32 accumulate in TMEM), bias added in the epilogue, output written
+ * token-major [B, T'*h*w, E] (the einsum 'ncts->ntsc' of vv:82 costs nothing).
+ * imgs [B,1,T,H,W] f32; weight [E, u*p*p] f32; bias [E] f32; out bf16|f32.  Requires p == 16, W % 16 == 0. */
+int oct_patch_embed_fwd(const float* imgs, const float* weight, const float* bias, void* out, int out_dtype, int64_t B,
+                        int64_t T, int64_t H, int64_t W, int64_t p, int64_t u, int64_t E, oct_stream_t stream);
+
+/* ---- kept-token gather + cls + separable pos-embed add (models:406-478) ------------------------------------
+ * out[b,0,:] = cls_row ; out[b,1+i,:] = x[b, ids_keep[b,i], :] + pos_sp[ids % G] + pos_tmp[ids / G]   (fp32 out)
+ * x [B,L,C] f32|bf16; pos_sp [G,C]; pos_tmp [L/G, C] or NULL (T'==1, models:437-440); cls_row [C] or NULL. */
+int oct_gather_tokens_fwd(const void* x, int x_dtype, const int64_t* ids_keep, const float* pos_sp, const float* pos_tmp,
+                          const float* cls_row, float* out, int64_t B, int64_t L, int64_t keep, int64_t G, int64_t C,
+                          oct_stream_t stream);
+/* backward: dx_keep [B*keep, C] (f32|bf16) = dout rows 1.. ; d_pos_sp [G,C], d_pos_tmp [L/G,C], d_cls_row [C] are
+ * deterministic segmented sums (overwritten). */
+int oct_gather_tokens_bwd(const float* dout, const int64_t* ids_keep, void* dx_keep, int dx_dtype, float* d_pos_sp,
+                          float* d_pos_tmp, float* d_cls_row, int64_t B, int64_t L, int64_t keep, int64_t G, int64_t C,
+                          oct_stream_t stream);
+
+/* ---- residual add + LayerNorm (FA:block.py:126-130,163-167; models:489,592) --------------------------------
+ * r = h (+ res_in) ; res_out = r (fp32, optional) ; y = LN(r)·gamma + beta ; mean/rstd saved ([M] fp32).
+ * h [M,C] f32|bf16 ; res_in/res_out [M,C] f32 or NULL ; y f32|bf16.  C % 4 == 0, C <= 8192. */
+int oct_add_ln_fwd(const void* h, int h_dtype, const float* res_in, float* res_out, const float* gamma,
+                   const float* beta, void* y, int y_dtype, float* mean, float* rstd, int64_t M, int64_t C, float eps,
+                   oct_stream_t stream);
+/* backward of the above.  x = the LN input that was normalised (res_out if it was written, else h).
+ * dx = LNbwd(dy) (+ dres_in) written as fp32 (dx_f32, optional) and/or low precision (dx_lp, optional);
+ * dgamma/dbeta [C] overwritten; ws: >= oct_add_ln_bwd_ws_bytes(M,C). */
+size_t oct_add_ln_bwd_ws_bytes(int64_t M, int64_t C);
+int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                   const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, int dx_lp_dtype, float* dgamma,
+                   float* dbeta, void* ws, size_t ws_bytes, int64_t M, int64_t C, oct_stream_t stream);
+
+/* ---- GEMM (replaces cuBLASLt for Wqkv/out_proj/fc1/fc2/decoder_embed/decoder_pred and their dgrad/wgrad) ----
+ * compute = OCT_BF16: A,B bf16, tcgen05.mma kind::f16, fp32 accumulate in TMEM, TMA-fed; D bf16|f32.
+ * compute = OCT_F32 : A,B,D f32, CUDA-core FFMA (parity mode).
+ * bias [N] f32 ; aux [M,ldd] same dtype as D (see epilogues) ; beta in {0,1} (1 only with fp32 D, EPI_NONE). */
+int oct_gemm(int compute, int layout, const void* A, const void* B, void* D, int d_dtype, int64_t M, int64_t N,
+             int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int epilogue, const float* bias, void* aux, int beta,
+             oct_stream_t stream);
+
+/* ---- self-attention on packed qkv (FA:mha.py:122-130 flash_attn_qkvpacked_func, non-causal, p=0) -----------
+ * qkv [B,S,3,H,d] ; out [B,S,H,d] ; lse [B,H,S] f32 (natural-log-sum-exp of scaled scores) ; scale = d^-0.5.
+ * compute = OCT_BF16: tcgen05 flash kernel (d in {32,64}); OCT_F32: fp32 CUDA-core kernel (d <= 128). */
+int oct_attn_fwd(int compute, const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H, int64_t d,
+                 float scale, oct_stream_t stream);
+size_t oct_attn_bwd_ws_bytes(int compute, int64_t B, int64_t S, int64_t H, int64_t d);
+int oct_attn_bwd(int compute, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
+                 size_t ws_bytes, int64_t B, int64_t S, int64_t H, int64_t d, float scale, oct_stream_t stream);
+
+/* ---- GELU (exact erf; FA:mlp.py:49) for the fp32 path; the bf16 path fuses it into the GEMM epilogues ------- */
+int oct_gelu_fwd(const void* x, void* y, int dtype, int64_t n, oct_stream_t stream);
+int oct_gelu_bwd(const void* dy, const void* x, void* dx, int dtype, int64_t n, oct_stream_t stream);
+
+/* ---- bias gradient: out[n] (= or +=) sum_m x[m,n] ; x [M,ldx] f32|bf16 ; deterministic two-stage ------------ */
+size_t oct_colsum_ws_bytes(int64_t M, int64_t N);
+int oct_colsum(const void* x, int x_dtype, float* out, int64_t M, int64_t N, int64_t ldx, int beta, void* ws,
+               size_t ws_bytes, oct_stream_t stream);
+
+/* ---- decoder un-shuffle + mask tokens + cls + separable pos add (models:515-573) --------------------------
+ * out[b,0] = cls_row ; out[b,1+j] = (r<keep ? y[b,r] : mask_token) + pos_sp[j % G] + pos_tmp[j / G], r = ids_restore[b,j]
+ * y [B,keep,D] f32|bf16 ; out [B,1+L,D] f32 (cls_row NULL -> no cls row, out [B,L,D]). */
+int oct_unshuffle_fwd(const void* y, int y_dtype, const int64_t* ids_restore, const float* mask_token,
+                      const float* pos_sp, const float* pos_tmp, const float* cls_row, float* out, int64_t B, int64_t L,
+                      int64_t keep, int64_t G, int64_t D, oct_stream_t stream);
+/* backward: dy [B,keep,D] ; d_mask_token [D], d_pos_sp [G,D], d_pos_tmp [L/G,D] (nullable), d_cls_row [D] (nullable)
+ * are deterministic sums (overwritten).  ws >= oct_unshuffle_bwd_ws_bytes(B,L,G,D). */
+size_t oct_unshuffle_bwd_ws_bytes(int64_t B, int64_t L, int64_t G, int64_t D);
+int oct_unshuffle_bwd(const float* dout, const int64_t* ids_restore, void* dy, int dy_dtype, float* d_mask_token,
+                      float* d_pos_sp, float* d_pos_tmp, float* d_cls_row, void* ws, size_t ws_bytes, int64_t B,
+                      int64_t L, int64_t keep, int64_t G, int64_t D, int has_cls, oct_stream_t stream);
+
+/* ---- forward_loss (models:613-667): masked MSE on (optionally per-patch normalised) pixels ------------------
+ * Reads the volume in place through patch indexing (no patchify copy).  imgs [B,1,T,H,W]; T_sel frames enter the loss
+ * (T_sel == T, or frame_idx [T_sel] = linspace(0,T-1,pred_t_dim).long() of models:630-640); u = t_pred_patch_size.  pred [B, pred_rows, P] with the token j at
+ * row (pred_row0 + j) (pred_row0 = 1 skips the cls row) ; mask [B,L] ; loss_tok [B,L] (workspace/out: per-patch mean
+ * squared error, 0 where mask==0) ; loss [1] ; mask_sum [1] ; frame_losses [B,T'] ; sums are reduced in a fixed order. */
+int oct_mse_loss_fwd(const float* imgs, const int64_t* frame_idx, const void* pred, int pred_dtype, const float* mask,
+                     float* loss_tok, float* loss, float* mask_sum, float* frame_losses, int64_t B, int64_t T, int64_t T_sel,
+                     int64_t H, int64_t W, int64_t p, int64_t u, int64_t pred_rows, int64_t pred_row0, int norm_pix,
+                     oct_stream_t stream);
+/* dpred [B,pred_rows,P] (rows < pred_row0 and kept tokens zero) = dloss · 2 (pred − target) · mask / (P · Σmask) */
+int oct_mse_loss_bwd(const float* imgs, const int64_t* frame_idx, const void* pred, int pred_dtype, const float* mask,
+                     const float* mask_sum, const float* dloss, void* dpred, int dpred_dtype, int64_t B, int64_t T,
+                     int64_t T_sel, int64_t H, int64_t W, int64_t p, int64_t u, int64_t pred_rows, int64_t pred_row0,
+                     int norm_pix, oct_stream_t stream);
+
+/* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
+int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTCUBE_B200_H */

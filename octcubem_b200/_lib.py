@@ -1,0 +1,80 @@
+"""ctypes binding of liboctcube_b200.so (the C ABI declared in include/octcube_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised (SURVEY §8b "Errors";
+mirrors the reference's fail-fast asserts, custom_util/video_vit.py:76-78).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboctcube_b200.so")
+
+OCT_F32, OCT_BF16, OCT_SIMT_BF16 = 0, 1, 2
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU = 0, 1, 2, 3
+
+P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+
+# name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
+SIGNATURES = {
+    "oct_version": (c_char_p, []),
+    "oct_last_error": (c_char_p, []),
+    "oct_device_info": (I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "oct_mask_sort": (I, [P, L, L, L, P, P, P, P]),
+    "oct_patchify": (I, [P, P, I, P, P, L, L, L, L, L, L, L, L, P]),
+    "oct_patch_embed_fwd": (I, [P, P, P, P, I, L, L, L, L, L, L, L, P]),
+    "oct_gather_tokens_fwd": (I, [P, I, P, P, P, P, P, L, L, L, L, L, P]),
+    "oct_gather_tokens_bwd": (I, [P, P, P, I, P, P, P, L, L, L, L, L, P]),
+    "oct_add_ln_fwd": (I, [P, I, P, P, P, P, P, I, P, P, L, L, F, P]),
+    "oct_add_ln_bwd_ws_bytes": (Z, [L, L]),
+    "oct_add_ln_bwd": (I, [P, I, P, I, P, P, P, P, P, P, I, P, P, P, Z, L, L, P]),
+    "oct_gemm": (I, [I, I, P, P, P, I, L, L, L, L, L, L, I, P, P, I, P]),
+    "oct_attn_fwd": (I, [I, P, P, P, L, L, L, L, F, P]),
+    "oct_attn_bwd_ws_bytes": (Z, [I, L, L, L, L]),
+    "oct_attn_bwd": (I, [I, P, P, P, P, P, P, Z, L, L, L, L, F, P]),
+    "oct_gelu_fwd": (I, [P, P, I, L, P]),
+    "oct_gelu_bwd": (I, [P, P, P, I, L, P]),
+    "oct_colsum_ws_bytes": (Z, [L, L]),
+    "oct_colsum": (I, [P, I, P, L, L, L, I, P, Z, P]),
+    "oct_unshuffle_fwd": (I, [P, I, P, P, P, P, P, P, L, L, L, L, L, P]),
+    "oct_unshuffle_bwd_ws_bytes": (Z, [L, L, L, L]),
+    "oct_unshuffle_bwd": (I, [P, P, P, I, P, P, P, P, P, Z, L, L, L, L, L, I, P]),
+    "oct_mse_loss_fwd": (I, [P, P, P, I, P, P, P, P, P, L, L, L, L, L, L, L, L, L, I, P]),
+    "oct_mse_loss_bwd": (I, [P, P, P, I, P, P, P, P, I, L, L, L, L, L, L, L, L, L, I, P]),
+    "oct_cast_f32_to_bf16": (I, [P, P, L, P]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"octcubem_b200: {LIB_PATH} not found — build it with `make -C octcubem_b200/csrc` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU/PyTorch fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().oct_last_error().decode()
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def version() -> str:
+    return load().oct_version().decode()

@@ -1,0 +1,51 @@
+// Library-level entry points: version, thread-local error string, device query.
+#include "common.cuh"
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+
+void oct_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int oct_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    oct_set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return OCT_OK;
+}
+
+int oct_num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    cached = p.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+extern "C" const char* oct_version(void) { return "octcube_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* oct_last_error(void) { return g_err; }
+
+extern "C" int oct_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { oct_set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return (int)e; }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) { oct_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return (int)e; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (p.major != 10) { oct_set_error("octcube_b200 needs an sm_100-class device, found sm_%d%d", p.major, p.minor); return OCT_ERR_UNSUPPORTED; }
+  return OCT_OK;
+}

@@ -1,0 +1,508 @@
+"""Tensor-level wrappers over the C ABI + the autograd Functions the model is built from.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every arithmetic op on the hot path is one
+of the hand-written kernels in csrc/ reached through liboctcube_b200.so.  No op in this file has a torch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE, GEMM_NN, GEMM_NT, GEMM_TN, OCT_BF16, OCT_F32,
+                   OCT_SIMT_BF16)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return OCT_F32
+    if t.dtype == torch.bfloat16:
+        return OCT_BF16
+    raise TypeError(f"octcubem_b200: unsupported dtype {t.dtype}")
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("octcubem_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("octcubem_b200 ops need contiguous tensors")
+
+
+def _call(name, *args):
+    rc = getattr(_lib.load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {_lib.last_error()}")
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def compute_of(dtype):
+    return OCT_F32 if dtype == torch.float32 else OCT_BF16
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# ----------------------------------------------------------------------------------------------------------------
+def mask_sort(noise: torch.Tensor, keep: int):
+    """random_masking's sort part (models_mae_joint_res_flash_attn.py:356-369) -> (mask f32, ids_restore i64, ids_keep i64)."""
+    _chk(noise)
+    assert noise.dtype == torch.float32 and noise.dim() == 2
+    B, L = noise.shape
+    ids_restore = torch.empty(B, L, dtype=torch.int64, device=noise.device)
+    ids_keep = torch.empty(B, keep, dtype=torch.int64, device=noise.device)
+    mask = torch.empty(B, L, dtype=torch.float32, device=noise.device)
+    _call("oct_mask_sort", _p(noise), B, L, keep, _p(ids_restore), _p(ids_keep), _p(mask), _stream())
+    return mask, ids_restore, ids_keep
+
+
+def patchify(imgs, p, u, out_dtype=torch.float32, ids_keep=None, frame_idx=None):
+    _chk(imgs, ids_keep, frame_idx)
+    B, C, T, H, W = imgs.shape
+    assert C == 1 and imgs.dtype == torch.float32
+    T_sel = T if frame_idx is None else frame_idx.numel()
+    L = (T_sel // u) * (H // p) * (W // p)
+    keep = 0 if ids_keep is None else ids_keep.shape[1]
+    rows = L if ids_keep is None else keep
+    out = torch.empty(B, rows, u * p * p, dtype=out_dtype, device=imgs.device)
+    _call("oct_patchify", _p(imgs), _p(out), _dt(out), _p(ids_keep), _p(frame_idx), B, T, H, W, p, u, T_sel, keep, _stream())
+    return out
+
+
+def patch_embed_tc(imgs, weight2d, bias, p, u, out_dtype=torch.bfloat16):
+    """Dense Conv3d patch embedding on tcgen05 (tf32), token-major output [B, L, E]."""
+    _chk(imgs, weight2d, bias)
+    B, C, T, H, W = imgs.shape
+    assert C == 1 and imgs.dtype == torch.float32 and weight2d.dtype == torch.float32
+    E = weight2d.shape[0]
+    L = (T // u) * (H // p) * (W // p)
+    out = torch.empty(B, L, E, dtype=out_dtype, device=imgs.device)
+    _call("oct_patch_embed_fwd", _p(imgs), _p(weight2d), _p(bias), _p(out), _dt(out), B, T, H, W, p, u, E, _stream())
+    return out
+
+
+def gemm(layout, A, B, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, aux=None, out=None, beta=0, compute=None):
+    """D[M,N] = op(A) op(B) (+ epilogue); see include/octcube_b200.h for the layouts.  A, B 2-D contiguous."""
+    _chk(A, B, bias, aux, out)
+    if compute is None:
+        compute = compute_of(A.dtype)
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    _call("oct_gemm", compute, layout, _p(A), _p(B), _p(out), _dt(out), M, N, K, A.stride(0), B.stride(0), out.stride(0),
+          epilogue, _p(bias), _p(aux), beta, _stream())
+    return out
+
+
+def colsum(x2d, out=None, beta=0):
+    _chk(x2d)
+    M, N = x2d.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x2d.device)
+    nb = _lib.load().oct_colsum_ws_bytes(M, N)
+    ws = _ws(nb, x2d.device)
+    _call("oct_colsum", _p(x2d), _dt(x2d), _p(out), M, N, x2d.stride(0), beta, _p(ws), ws.numel(), _stream())
+    return out
+
+
+def add_ln_fwd(h, res_in, gamma, beta, eps, y_dtype, want_res_out):
+    _chk(h, res_in, gamma, beta)
+    C = h.shape[-1]
+    M = h.numel() // C
+    y = torch.empty(h.shape, dtype=y_dtype, device=h.device)
+    res_out = torch.empty(h.shape, dtype=torch.float32, device=h.device) if want_res_out else None
+    mean = torch.empty(M, dtype=torch.float32, device=h.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=h.device)
+    _call("oct_add_ln_fwd", _p(h), _dt(h), _p(res_in), _p(res_out), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd),
+          M, C, float(eps), _stream())
+    return y, res_out, mean, rstd
+
+
+def add_ln_bwd(dy, x, mean, rstd, gamma, dres_in, want_f32, want_lp):
+    _chk(dy, x, mean, rstd, gamma, dres_in)
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx_f32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
+    dx_lp = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_lp else None
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+    nb = _lib.load().oct_add_ln_bwd_ws_bytes(M, C)
+    ws = _ws(nb, x.device)
+    _call("oct_add_ln_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres_in), _p(dx_f32), _p(dx_lp),
+          OCT_BF16, _p(dgamma), _p(dbeta), _p(ws), ws.numel(), M, C, _stream())
+    return dx_f32, dx_lp, dgamma, dbeta
+
+
+def attn_fwd(qkv, H, d, compute):
+    _chk(qkv)
+    B, S = qkv.shape[0], qkv.shape[1]
+    out = torch.empty(B, S, H * d, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(B, H, S, dtype=torch.float32, device=qkv.device)
+    _call("oct_attn_fwd", compute, _p(qkv), _p(out), _p(lse), B, S, H, d, 1.0 / math.sqrt(d), _stream())
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, H, d, compute):
+    _chk(qkv, out, dout, lse)
+    B, S = qkv.shape[0], qkv.shape[1]
+    dqkv = torch.empty_like(qkv)
+    nb = _lib.load().oct_attn_bwd_ws_bytes(compute, B, S, H, d)
+    ws = _ws(nb, qkv.device)
+    _call("oct_attn_bwd", compute, _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(ws), ws.numel(), B, S, H, d,
+          1.0 / math.sqrt(d), _stream())
+    return dqkv
+
+
+def gelu_fwd(x):
+    _chk(x)
+    y = torch.empty_like(x)
+    _call("oct_gelu_fwd", _p(x), _p(y), _dt(x), x.numel(), _stream())
+    return y
+
+
+def gelu_bwd(dy, x):
+    _chk(dy, x)
+    dx = torch.empty_like(x)
+    _call("oct_gelu_bwd", _p(dy), _p(x), _p(dx), _dt(x), x.numel(), _stream())
+    return dx
+
+
+def cast_bf16(src_f32, dst_bf16=None):
+    _chk(src_f32, dst_bf16)
+    if dst_bf16 is None:
+        dst_bf16 = torch.empty(src_f32.shape, dtype=torch.bfloat16, device=src_f32.device)
+    _call("oct_cast_f32_to_bf16", _p(src_f32), _p(dst_bf16), src_f32.numel(), _stream())
+    return dst_bf16
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# autograd Functions
+# ----------------------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (nn.Linear; flash_attn/modules/mha.py:635,703, models:511,595).  `w_lp` is the bf16 shadow of `weight`
+    used by the tensor-core path (None in fp32 mode).  Grad of weight/bias is fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_lp):
+        w = weight if w_lp is None else w_lp
+        assert x.dtype == w.dtype, (x.dtype, w.dtype)
+        N, K = w.shape
+        x2 = x.reshape(-1, K)
+        M = x2.shape[0]
+        y = gemm(GEMM_NT, x2, w, M, N, K, x.dtype, EPI_BIAS, bias=bias)
+        ctx.save_for_backward(x2, w)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        M = x2.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(GEMM_NN, dy2, w, M, K, N, x2.dtype).view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = gemm(GEMM_TN, dy2, x2, N, K, M, torch.float32)
+        if ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dw, db, None
+
+
+class MlpFn(torch.autograd.Function):
+    """fc1 -> GELU(erf) -> fc2 (flash_attn/modules/mlp.py:47-51).  GELU is fused into the fc1 epilogue and its derivative
+    into the fc2-dgrad epilogue (bf16 and fp32 paths alike)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w1_lp, w2_lp):
+        wa = w1 if w1_lp is None else w1_lp
+        wb = w2 if w2_lp is None else w2_lp
+        hid, dim = wa.shape
+        x2 = x.reshape(-1, dim)
+        M = x2.shape[0]
+        pre = torch.empty(M, hid, dtype=x.dtype, device=x.device)
+        act = gemm(GEMM_NT, x2, wa, M, hid, dim, x.dtype, EPI_BIAS_GELU, bias=b1, aux=pre)
+        y = gemm(GEMM_NT, act, wb, M, wb.shape[0], hid, x.dtype, EPI_BIAS, bias=b2)
+        ctx.save_for_backward(x2, wa, wb, pre, act)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], wb.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wa, wb, pre, act = ctx.saved_tensors
+        hid, dim = wa.shape
+        out_dim = wb.shape[0]
+        dy2 = dy.reshape(-1, out_dim)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        M = x2.shape[0]
+        dpre = gemm(GEMM_NN, dy2, wb, M, hid, out_dim, x2.dtype, EPI_DGELU, aux=pre)
+        dw2 = gemm(GEMM_TN, dy2, act, out_dim, hid, M, torch.float32)
+        db2 = colsum(dy2)
+        dx = gemm(GEMM_NN, dpre, wa, M, dim, hid, x2.dtype).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw1 = gemm(GEMM_TN, dpre, x2, hid, dim, M, torch.float32)
+        db1 = colsum(dpre)
+        return dx, dw1, db1, dw2, db2, None, None
+
+
+class AttnFn(torch.autograd.Function):
+    """flash_attn_qkvpacked_func(qkv, 0.0, softmax_scale=d^-0.5, causal=False) (flash_attn/modules/mha.py:122-130)."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, compute):
+        B, S, three_dim = qkv.shape
+        d = three_dim // (3 * H)
+        out, lse = attn_fwd(qkv, H, d, compute)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.H, ctx.d, ctx.compute = H, d, compute
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        return attn_bwd(qkv, out, dout, lse, ctx.H, ctx.d, ctx.compute), None, None
+
+
+class AddLNFn(torch.autograd.Function):
+    """residual = h (+ residual_in);  y = LayerNorm(residual)  (flash_attn/modules/block.py:126-130,163-167).
+    Returns (y, residual fp32).  With residual_in=None and fp32 h the residual IS h (block 0) and is not copied.
+    keep_residual=False is the final-norm case (models:489,592): only y is produced (quirk Q1)."""
+
+    @staticmethod
+    def forward(ctx, h, res_in, gamma, beta, eps, y_dtype, keep_residual):
+        if res_in is not None and not keep_residual:
+            raise RuntimeError("AddLNFn: res_in given but residual not kept")
+        y, res_out, mean, rstd = add_ln_fwd(h, res_in, gamma, beta, eps, y_dtype, keep_residual)
+        x = res_out if keep_residual else h  # the tensor that was normalised
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.h_dtype = h.dtype
+        ctx.has_res_in = res_in is not None
+        return y, res_out
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        if dres is not None and not dres.is_contiguous():
+            dres = dres.contiguous()
+        h_lp = ctx.h_dtype == torch.bfloat16
+        want_f32 = ctx.has_res_in or not h_lp
+        dx_f32, dx_lp, dgamma, dbeta = add_ln_bwd(dy, x, mean, rstd, gamma, dres, want_f32, h_lp)
+        dh = dx_lp if h_lp else dx_f32
+        dres_in = dx_f32 if ctx.has_res_in else None
+        return dh, dres_in, dgamma, dbeta, None, None, None
+
+
+class GatherTokensFn(torch.autograd.Function):
+    """x_masked + cls + pos (models:406-478): out[b,0]=cls_row; out[b,1+i] = x[b,ids_keep[b,i]] + pos_sp[s] + pos_tmp[t].
+    x is the dense patch-embed output; its gradient is returned as a dense tensor only if required (standalone use);
+    the fused encoder path uses EmbedTokensFn below, which never materialises the dense gradient."""
+
+    @staticmethod
+    def forward(ctx, x, ids_keep, pos_sp, pos_tmp, cls_row):
+        _chk(x, ids_keep, pos_sp, pos_tmp, cls_row)
+        B, L, C = x.shape
+        keep = ids_keep.shape[1]
+        G = pos_sp.shape[0] if pos_sp is not None else L
+        out = torch.empty(B, keep + (1 if cls_row is not None else 0), C, dtype=torch.float32, device=x.device)
+        _call("oct_gather_tokens_fwd", _p(x), _dt(x), _p(ids_keep), _p(pos_sp), _p(pos_tmp), _p(cls_row), _p(out), B, L, keep,
+              G, C, _stream())
+        ctx.save_for_backward(ids_keep)
+        ctx.dims = (B, L, keep, G, C, x.dtype, pos_sp is not None, pos_tmp is not None, cls_row is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids_keep,) = ctx.saved_tensors
+        B, L, keep, G, C, xdt, has_sp, has_tmp, has_cls = ctx.dims
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dev = dout.device
+        dxk = torch.empty(B * keep, C, dtype=xdt, device=dev)
+        d_sp = torch.empty(G, C, dtype=torch.float32, device=dev) if has_sp else None
+        d_tmp = torch.empty(L // G, C, dtype=torch.float32, device=dev) if has_tmp else None
+        d_cls = torch.empty(C, dtype=torch.float32, device=dev) if has_cls else None
+        _call("oct_gather_tokens_bwd", _p(dout), _p(ids_keep), _p(dxk), _dt(dxk), _p(d_sp), _p(d_tmp), _p(d_cls), B, L, keep, G,
+              C, _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.zeros(B, L, C, dtype=xdt, device=dev)
+            dx.scatter_(1, ids_keep.unsqueeze(-1).expand(-1, -1, C), dxk.view(B, keep, C))  # standalone use only
+        return dx, None, d_sp, d_tmp, d_cls
+
+
+class EmbedTokensFn(torch.autograd.Function):
+    """Fused encoder front end: PatchEmbed (vv:74-83) -> random_masking gather (models:362-363) -> cls + pos add
+    (models:409-478).  Forward runs the dense im2col-free tcgen05 patch-embed (bf16 mode) or patchify + fp32 GEMM
+    (fp32 mode).  Backward touches only the kept tokens: dW = dX_keep^T · patches_keep, db = colsum(dX_keep)."""
+
+    @staticmethod
+    def forward(ctx, imgs, weight, bias, ids_keep, pos_sp, pos_tmp, cls_row, p, u, act_dtype):
+        _chk(imgs, weight, bias, ids_keep, pos_sp, pos_tmp, cls_row)
+        B, _, T, H, W = imgs.shape
+        E = weight.shape[0]
+        w2d = weight.view(E, -1)
+        if act_dtype == torch.bfloat16:
+            x = patch_embed_tc(imgs, w2d, bias, p, u, torch.bfloat16)
+        else:
+            patches = patchify(imgs, p, u, torch.float32)
+            L = patches.shape[1]
+            x = gemm(GEMM_NT, patches.view(B * L, -1), w2d, B * L, E, w2d.shape[1], torch.float32, EPI_BIAS, bias=bias)
+            x = x.view(B, L, E)
+        L = x.shape[1]
+        keep = ids_keep.shape[1]
+        G = pos_sp.shape[0]
+        out = torch.empty(B, keep + (1 if cls_row is not None else 0), E, dtype=torch.float32, device=imgs.device)
+        _call("oct_gather_tokens_fwd", _p(x), _dt(x), _p(ids_keep), _p(pos_sp), _p(pos_tmp), _p(cls_row), _p(out), B, L, keep,
+              G, E, _stream())
+        ctx.save_for_backward(imgs, ids_keep)
+        ctx.dims = (B, L, keep, G, E, p, u, act_dtype, pos_tmp is not None, cls_row is not None, tuple(weight.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        imgs, ids_keep = ctx.saved_tensors
+        B, L, keep, G, E, p, u, act_dtype, has_tmp, has_cls, wshape = ctx.dims
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dev = dout.device
+        dxk = torch.empty(B * keep, E, dtype=act_dtype, device=dev)
+        d_sp = torch.empty(G, E, dtype=torch.float32, device=dev)
+        d_tmp = torch.empty(L // G, E, dtype=torch.float32, device=dev) if has_tmp else None
+        d_cls = torch.empty(E, dtype=torch.float32, device=dev) if has_cls else None
+        _call("oct_gather_tokens_bwd", _p(dout), _p(ids_keep), _p(dxk), _dt(dxk), _p(d_sp), _p(d_tmp), _p(d_cls), B, L, keep, G,
+              E, _stream())
+        pk = patchify(imgs, p, u, act_dtype, ids_keep=ids_keep).view(B * keep, -1)
+        dw = gemm(GEMM_TN, dxk, pk, E, pk.shape[1], B * keep, torch.float32).view(wshape)
+        db = colsum(dxk)
+        return None, dw, db, None, d_sp, d_tmp, d_cls, None, None, None
+
+
+class UnshuffleFn(torch.autograd.Function):
+    """Decoder input assembly (models:515-573): mask tokens + un-shuffle by ids_restore + decoder cls + pos add."""
+
+    @staticmethod
+    def forward(ctx, y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row):
+        _chk(y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row)
+        B, keep, D = y.shape
+        L = ids_restore.shape[1]
+        G = pos_sp.shape[0]
+        has_cls = cls_row is not None
+        out = torch.empty(B, L + (1 if has_cls else 0), D, dtype=torch.float32, device=y.device)
+        _call("oct_unshuffle_fwd", _p(y), _dt(y), _p(ids_restore), _p(mask_token), _p(pos_sp), _p(pos_tmp), _p(cls_row), _p(out),
+              B, L, keep, G, D, _stream())
+        ctx.save_for_backward(ids_restore)
+        ctx.dims = (B, L, keep, G, D, y.dtype, pos_tmp is not None, has_cls)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids_restore,) = ctx.saved_tensors
+        B, L, keep, G, D, ydt, has_tmp, has_cls = ctx.dims
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dev = dout.device
+        dy = torch.empty(B, keep, D, dtype=ydt, device=dev)
+        d_mt = torch.empty(D, dtype=torch.float32, device=dev)
+        d_sp = torch.empty(G, D, dtype=torch.float32, device=dev)
+        d_tmp = torch.empty(L // G, D, dtype=torch.float32, device=dev) if has_tmp else None
+        d_cls = torch.empty(D, dtype=torch.float32, device=dev) if has_cls else None
+        nb = _lib.load().oct_unshuffle_bwd_ws_bytes(B, L, G, D)
+        ws = _ws(nb, dev)
+        _call("oct_unshuffle_bwd", _p(dout), _p(ids_restore), _p(dy), _dt(dy), _p(d_mt), _p(d_sp), _p(d_tmp), _p(d_cls), _p(ws),
+              ws.numel(), B, L, keep, G, D, 1 if has_cls else 0, _stream())
+        return dy, None, d_mt, d_sp, d_tmp, d_cls
+
+
+class MaskedMSELossFn(torch.autograd.Function):
+    """forward_loss (models:613-667).  pred_full [B, row0 + L, P] (row0 = 1: the cls row is skipped in place).
+    Returns (loss, frame_losses); frame_losses carries no gradient (the engine only logs it, engine_pretrain.py:133-146)."""
+
+    @staticmethod
+    def forward(ctx, imgs, pred_full, mask, p, u, row0, norm_pix, frame_idx):
+        _chk(imgs, pred_full, mask, frame_idx)
+        B, _, T, H, W = imgs.shape
+        T_sel = T if frame_idx is None else frame_idx.numel()
+        Tp = T_sel // u
+        L = mask.shape[1]
+        dev = imgs.device
+        loss_tok = torch.empty(B, L, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        msum = torch.empty((), dtype=torch.float32, device=dev)
+        frame = torch.empty(B, Tp, dtype=torch.float32, device=dev)
+        _call("oct_mse_loss_fwd", _p(imgs), _p(frame_idx), _p(pred_full), _dt(pred_full), _p(mask), _p(loss_tok), _p(loss),
+              _p(msum), _p(frame), B, T, T_sel, H, W, p, u, pred_full.shape[1], row0, 1 if norm_pix else 0, _stream())
+        ctx.save_for_backward(imgs, pred_full, mask, msum, frame_idx if frame_idx is not None else torch.empty(0, device=dev))
+        ctx.cfg = (p, u, row0, norm_pix, frame_idx is not None)
+        ctx.mark_non_differentiable(frame)
+        return loss, frame
+
+    @staticmethod
+    def backward(ctx, dloss, _dframe):
+        imgs, pred_full, mask, msum, frame_idx = ctx.saved_tensors
+        p, u, row0, norm_pix, has_idx = ctx.cfg
+        if not has_idx:
+            frame_idx = None
+        B, _, T, H, W = imgs.shape
+        T_sel = T if frame_idx is None else frame_idx.numel()
+        dloss = dloss.to(torch.float32).contiguous()
+        dpred = torch.empty_like(pred_full)
+        _call("oct_mse_loss_bwd", _p(imgs), _p(frame_idx), _p(pred_full), _dt(pred_full), _p(mask), _p(msum), _p(dloss), _p(dpred),
+              _dt(dpred), B, T, T_sel, H, W, p, u, pred_full.shape[1], row0, 1 if norm_pix else 0, _stream())
+        return None, dpred, None, None, None, None, None, None
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """Standalone PatchEmbed.forward (vv:74-83) -> [B, T'*h*w, E] with a dense backward (wgrad over all tokens)."""
+
+    @staticmethod
+    def forward(ctx, imgs, weight, bias, p, u, act_dtype):
+        _chk(imgs, weight, bias)
+        B = imgs.shape[0]
+        E = weight.shape[0]
+        w2d = weight.view(E, -1)
+        if act_dtype == torch.bfloat16:
+            x = patch_embed_tc(imgs, w2d, bias, p, u, torch.bfloat16)
+        else:
+            patches = patchify(imgs, p, u, torch.float32)
+            L = patches.shape[1]
+            x = gemm(GEMM_NT, patches.view(B * L, -1), w2d, B * L, E, w2d.shape[1], torch.float32, EPI_BIAS, bias=bias)
+            x = x.view(B, L, E)
+        ctx.save_for_backward(imgs)
+        ctx.cfg = (p, u, act_dtype, tuple(weight.shape))
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        (imgs,) = ctx.saved_tensors
+        p, u, act_dtype, wshape = ctx.cfg
+        if not dx.is_contiguous():
+            dx = dx.contiguous()
+        B, L, E = dx.shape
+        patches = patchify(imgs, p, u, act_dtype).view(B * L, -1)
+        dx2 = dx.view(B * L, E)
+        dw = gemm(GEMM_TN, dx2, patches, E, patches.shape[1], B * L, torch.float32).view(wshape)
+        db = colsum(dx2)
+        return None, dw, db, None, None, None

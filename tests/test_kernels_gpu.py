@@ -1,0 +1,285 @@
+"""GPU parity tests of the individual kernels (through the C ABI) against CPU/torch fp32-or-better references."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from octcubem_b200 import ops  # noqa: E402
+from octcubem_b200._lib import EPI_BIAS, GEMM_NN, GEMM_NT, GEMM_TN, OCT_BF16, OCT_F32  # noqa: E402
+from oracle import mae3d_oracle as O  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ---------------------------------------------------------------- masking: bit-exact (integer work)
+@pytest.mark.parametrize("L", [1024, 4096, 5120])
+@pytest.mark.parametrize("kind", ["natural", "tiefree", "quantized"])
+def test_mask_sort_golden(golden_dir, L, kind):
+    g = np.load(os.path.join(golden_dir, "masking_cases.npz"))
+    noise = torch.from_numpy(g[f"{kind}_{L}_noise"]).to(DEV)
+    keep = g[f"{kind}_{L}_ids_keep"].shape[1]
+    mask, ids_restore, ids_keep = ops.mask_sort(noise, keep)
+    assert ids_restore.dtype == torch.int64 and ids_keep.dtype == torch.int64 and mask.dtype == torch.float32
+    assert np.array_equal(ids_restore.cpu().numpy(), g[f"{kind}_{L}_ids_restore"].astype(np.int64))
+    assert np.array_equal(ids_keep.cpu().numpy(), g[f"{kind}_{L}_ids_keep"].astype(np.int64))
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), g[f"{kind}_{L}_mask"])
+
+
+@pytest.mark.parametrize("B,L,keep", [(1, 1, 0), (1, 1, 1), (3, 7, 3), (8, 5120, 511), (2, 16384, 1638), (64, 1024, 256), (2, 333, 333)])
+def test_mask_sort_vs_oracle_and_torch_cuda(B, L, keep):
+    g = torch.Generator().manual_seed(L + keep)
+    noise = torch.rand(B, L, generator=g)
+    noise[:, L // 3:] = torch.floor(noise[:, L // 3:] * 50) / 50  # plenty of ties
+    mask, ids_restore, ids_keep = ops.mask_sort(noise.to(DEV), keep)
+    sh = torch.argsort(noise, dim=1, stable=True)
+    rs = torch.argsort(sh, dim=1, stable=True)
+    assert torch.equal(ids_restore.cpu(), rs)
+    assert torch.equal(ids_keep.cpu(), sh[:, :keep])
+    assert torch.equal(mask.cpu(), (rs >= keep).float())
+    # the contract of SURVEY H1: equals what the reference computes on ITS device (torch.argsort on CUDA, radix = stable)
+    sh_cuda = torch.argsort(noise.to(DEV), dim=1)
+    assert torch.equal(torch.argsort(sh_cuda, dim=1).cpu(), ids_restore.cpu())
+
+
+def test_mask_sort_special_values_and_identity():
+    noise = torch.tensor([[0.0, -0.0, float("inf"), -float("inf"), 1.0, -1.0, 0.0, 1.0]])
+    mask, ids_restore, ids_keep = ops.mask_sort(noise.to(DEV), 3)
+    sh = torch.argsort(noise, dim=1, stable=True)
+    assert torch.equal(ids_restore.cpu(), torch.argsort(sh, dim=1, stable=True))
+    ar = torch.arange(100, dtype=torch.float32).expand(2, 100).contiguous()  # mask_ratio == 0 path (models...:350-352)
+    mask, ids_restore, ids_keep = ops.mask_sort(ar.to(DEV), 100)
+    assert torch.equal(ids_restore.cpu(), torch.arange(100).expand(2, 100)) and float(mask.sum()) == 0
+
+
+def test_mask_sort_empty():
+    m, r, k = ops.mask_sort(torch.empty(0, 16, device=DEV), 4)
+    assert r.shape == (0, 16) and k.shape == (0, 4)
+
+
+# ---------------------------------------------------------------- patchify / gather / unshuffle (pure copies: exact)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify_exact(dtype):
+    imgs = torch.rand(2, 1, 6, 64, 48)
+    want = O.patchify(imgs, 16, 3)
+    got = ops.patchify(imgs.to(DEV), 16, 3, dtype)
+    assert torch.equal(got.cpu(), want.to(dtype))
+    ids = torch.stack([torch.randperm(want.shape[1])[:5] for _ in range(2)])
+    gk = ops.patchify(imgs.to(DEV), 16, 3, dtype, ids_keep=ids.to(DEV))
+    assert torch.equal(gk.cpu(), torch.gather(want, 1, ids[..., None].expand(-1, -1, 768)).to(dtype))
+    fidx = torch.tensor([0, 2, 5])
+    gf = ops.patchify(imgs.to(DEV), 16, 3, dtype, frame_idx=fidx.to(DEV))
+    assert torch.equal(gf.cpu(), O.patchify(imgs[:, :, fidx], 16, 3).to(dtype))
+
+
+@pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Tp", [1, 4])
+def test_gather_tokens_fwd_bwd(xdtype, Tp):
+    B, G, C, keep = 3, 16, 64, 7
+    L = Tp * G
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, L, C, generator=g).to(xdtype)
+    ids = torch.stack([torch.randperm(L, generator=g)[:keep] for _ in range(B)])
+    sp = torch.randn(G, C, generator=g, requires_grad=True)
+    tmp = torch.randn(Tp, C, generator=g, requires_grad=True) if Tp > 1 else None
+    cls = torch.randn(C, generator=g, requires_grad=True)
+    xr = x.float().requires_grad_(True)
+    pos = sp.repeat(Tp, 1) + (torch.repeat_interleave(tmp, G, dim=0) if tmp is not None else 0)
+    want = torch.cat([cls.expand(B, 1, C), torch.gather(xr, 1, ids[..., None].expand(-1, -1, C)) + pos[ids]], 1)
+    dout = torch.randn(B, keep + 1, C, generator=g)
+    want.backward(dout)
+    xd = x.to(DEV).requires_grad_(True)
+    spd, clsd = sp.detach().to(DEV).requires_grad_(True), cls.detach().to(DEV).requires_grad_(True)
+    tmpd = tmp.detach().to(DEV).requires_grad_(True) if tmp is not None else None
+    got = ops.GatherTokensFn.apply(xd, ids.to(DEV), spd, tmpd, clsd)
+    assert rel(got, want.detach()) < 1e-6
+    got.backward(dout.to(DEV))
+    assert rel(spd.grad, sp.grad) < 1e-6 and rel(clsd.grad, cls.grad) < 1e-6
+    if tmp is not None:
+        assert rel(tmpd.grad, tmp.grad) < 1e-6
+    assert rel(xd.grad.float(), xr.grad.to(xdtype).float()) < 1e-6
+
+
+@pytest.mark.parametrize("ydtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Tp", [1, 4])
+def test_unshuffle_fwd_bwd(ydtype, Tp):
+    B, G, D, keep = 2, 16, 32, 6
+    L = Tp * G
+    g = torch.Generator().manual_seed(1)
+    y = torch.randn(B, keep, D, generator=g).to(ydtype)
+    ids_restore = torch.stack([torch.randperm(L, generator=g) for _ in range(B)])
+    mt = torch.randn(D, generator=g, requires_grad=True)
+    sp = torch.randn(G, D, generator=g, requires_grad=True)
+    tmp = torch.randn(Tp, D, generator=g, requires_grad=True) if Tp > 1 else None
+    cls = torch.randn(D, generator=g, requires_grad=True)
+    yr = y.float().requires_grad_(True)
+    x_ = torch.cat([yr, mt.expand(B, L - keep, D)], 1)
+    x_ = torch.gather(x_, 1, ids_restore[..., None].expand(-1, -1, D))
+    pos = sp.repeat(Tp, 1) + (torch.repeat_interleave(tmp, G, dim=0) if tmp is not None else 0)
+    want = torch.cat([cls.expand(B, 1, D), x_ + pos], 1)
+    dout = torch.randn(B, L + 1, D, generator=g)
+    want.backward(dout)
+    yd = y.to(DEV).requires_grad_(True)
+    leaves = [t.detach().to(DEV).requires_grad_(True) if t is not None else None for t in (mt, sp, tmp, cls)]
+    got = ops.UnshuffleFn.apply(yd, ids_restore.to(DEV), leaves[0], leaves[1], leaves[2], leaves[3])
+    assert rel(got, want.detach()) < 1e-6
+    got.backward(dout.to(DEV))
+    for a, b in zip(leaves, (mt, sp, tmp, cls)):
+        if a is not None:
+            assert rel(a.grad, b.grad) < 1e-5
+    assert rel(yd.grad.float(), yr.grad.to(ydtype).float()) < 1e-6
+
+
+# ---------------------------------------------------------------- add + LayerNorm
+@pytest.mark.parametrize("C", [32, 64, 512, 1024, 1280])
+@pytest.mark.parametrize("hdtype,ydtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+def test_add_ln_fwd_bwd(C, hdtype, ydtype):
+    M = 77
+    g = torch.Generator().manual_seed(C)
+    h = (torch.randn(M, C, generator=g) * 2 + 0.5).to(hdtype)
+    res = torch.randn(M, C, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    hr, rr = h.float().requires_grad_(True), res.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    r_ref = hr + rr
+    y_ref = F.layer_norm(r_ref, (C,), gr, br, 1e-6)
+    dy, dres = torch.randn(M, C, generator=g).to(ydtype), torch.randn(M, C, generator=g)
+    (y_ref * dy.float()).sum().backward(retain_graph=True)
+    r_ref.backward(dres)
+    hd, rd = h.to(DEV).requires_grad_(True), res.to(DEV).requires_grad_(True)
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y, r = ops.AddLNFn.apply(hd, rd, gd, bd, 1e-6, ydtype, True)
+    tol = 1e-5 if ydtype == torch.float32 else 6e-3
+    assert rel(y, y_ref.detach()) < tol and rel(r, r_ref.detach()) < 1e-6
+    torch.autograd.backward([y, r], [dy.to(DEV), dres.to(DEV)])
+    btol = 1e-4 if hdtype == torch.float32 else 6e-3
+    assert rel(rd.grad, rr.grad) < 1e-4 and rel(hd.grad, hr.grad) < btol
+    assert rel(gd.grad, gr.grad) < 1e-4 and rel(bd.grad, br.grad) < 1e-4
+
+
+def test_ln_only_final_norm_form():
+    M, C = 50, 64
+    h = torch.randn(M, C).bfloat16()
+    gamma, beta = torch.randn(C), torch.randn(C)
+    y, r = ops.AddLNFn.apply(h.to(DEV), None, gamma.to(DEV), beta.to(DEV), 1e-6, torch.bfloat16, False)
+    assert r is None
+    assert rel(y, F.layer_norm(h.float(), (C,), gamma, beta, 1e-6)) < 6e-3
+
+
+# ---------------------------------------------------------------- GELU / colsum / cast
+def test_gelu_colsum_cast():
+    x = torch.randn(64, 256) * 3
+    xr = x.clone().requires_grad_(True)
+    F.gelu(xr).sum().backward()
+    assert rel(ops.gelu_fwd(x.to(DEV)), F.gelu(x)) < 1e-6
+    assert rel(ops.gelu_bwd(torch.ones_like(x).to(DEV), x.to(DEV)), xr.grad) < 1e-5
+    big = torch.randn(5000, 136)
+    assert rel(ops.colsum(big.to(DEV)), big.double().sum(0)) < 1e-5
+    assert rel(ops.colsum(big.bfloat16().to(DEV)), big.bfloat16().double().sum(0)) < 1e-5
+    assert torch.equal(ops.cast_bf16(big.to(DEV)).cpu(), big.bfloat16())
+    odd = torch.randn(1027)
+    assert torch.equal(ops.cast_bf16(odd.to(DEV)).cpu(), odd.bfloat16())
+
+
+# ---------------------------------------------------------------- loss
+@pytest.mark.parametrize("norm_pix", [False, True])
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
+def test_mse_loss_fwd_bwd(norm_pix, pdtype):
+    cfg = O.MAEConfig(input_size=64, num_frames=12, pred_t_dim=12, norm_pix_loss=norm_pix)
+    B, L, P = 2, 4 * 16, 768
+    g = torch.Generator().manual_seed(5)
+    imgs = O.synthetic_volume(B, 12, 64, 64, seed=2, zero_pad_frames=1)
+    pred_full = torch.randn(B, L + 1, P, generator=g).to(pdtype)
+    mask = (torch.rand(B, L, generator=g) > 0.2).float()
+    pr = pred_full.float().requires_grad_(True)
+    loss_ref, fl_ref = O.forward_loss(cfg, imgs, pr[:, 1:], mask, frame_loss=True)
+    (loss_ref * 1.7).backward()
+    pd = pred_full.to(DEV).requires_grad_(True)
+    loss, fl = ops.MaskedMSELossFn.apply(imgs.to(DEV), pd, mask.to(DEV), 16, 3, 1, norm_pix, None)
+    assert abs(float(loss) - float(loss_ref)) < 2e-6 * abs(float(loss_ref))
+    assert rel(fl, fl_ref.detach()) < 1e-5
+    (loss * 1.7).backward()
+    assert rel(pd.grad.float(), pr.grad) < (1e-5 if pdtype == torch.float32 else 5e-3)
+    assert float(pd.grad[:, 0].abs().max()) == 0.0
+
+
+def test_mse_loss_frame_index_select():
+    # pred_t_dim != T: linspace index_select of models...:630-640
+    cfg = O.MAEConfig(input_size=64, num_frames=12, pred_t_dim=6, t_patch_size=2)  # u = 1, T' = 6
+    imgs = O.synthetic_volume(1, 12, 64, 64, seed=4, zero_pad_frames=0)
+    L, P = 6 * 16, 256
+    pred = torch.randn(1, L, P)
+    mask = torch.ones(1, L)
+    want = O.forward_loss(cfg, imgs, pred, mask)
+    fidx = torch.linspace(0, 11, 6).long()
+    loss, _ = ops.MaskedMSELossFn.apply(imgs.to(DEV), pred.to(DEV), mask.to(DEV), 16, 1, 0, False, fidx.to(DEV))
+    assert abs(float(loss) - float(want)) < 2e-6 * abs(float(want))
+
+
+# ---------------------------------------------------------------- GEMMs / attention / patch-embed
+@pytest.mark.parametrize("layout", [GEMM_NT, GEMM_NN, GEMM_TN])
+@pytest.mark.parametrize("compute,M,N,K", [(OCT_F32, 130, 72, 40), (OCT_BF16, 384, 768, 512), (OCT_BF16, 3280, 1024, 1024),
+                                           (OCT_BF16, 200, 136, 72), (OCT_BF16, 4097, 512, 512)])
+def test_gemm(layout, compute, M, N, K):
+    g = torch.Generator().manual_seed(M)
+    dt = torch.float32 if compute == OCT_F32 else torch.bfloat16
+    a, b = torch.randn(M, K, generator=g).to(dt), torch.randn(N, K, generator=g).to(dt)
+    A = a.to(DEV) if layout != GEMM_TN else a.t().contiguous().to(DEV)
+    Bm = b.to(DEV) if layout == GEMM_NT else b.t().contiguous().to(DEV)
+    out = ops.gemm(layout, A, Bm, M, N, K, torch.float32, compute=compute)
+    assert rel(out, a.double() @ b.double().t()) < 2e-6
+
+
+def test_linear_and_mlp_functions_bf16():
+    g = torch.Generator().manual_seed(9)
+    M, dim, hid = 300, 128, 512
+    x = torch.randn(M, dim, generator=g)
+    w1, b1 = torch.randn(hid, dim, generator=g) * 0.1, torch.randn(hid, generator=g) * 0.1
+    w2, b2 = torch.randn(dim, hid, generator=g) * 0.1, torch.randn(dim, generator=g) * 0.1
+    leaves = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    y_ref = F.linear(F.gelu(F.linear(leaves[0], leaves[1], leaves[2])), leaves[3], leaves[4])
+    dy = torch.randn(M, dim, generator=g)
+    y_ref.backward(dy)
+    d = [t.to(DEV).requires_grad_(True) for t in (x.bfloat16(), w1, b1, w2, b2)]
+    y = ops.MlpFn.apply(d[0], d[1], d[2], d[3], d[4], d[1].detach().bfloat16(), d[3].detach().bfloat16())
+    assert rel(y.float(), y_ref.detach()) < 1e-2
+    y.backward(dy.bfloat16().to(DEV))
+    for got, want in zip(d, leaves):
+        assert rel(got.grad.float(), want.grad) < 2e-2
+
+
+@pytest.mark.parametrize("compute,dtype,tol", [(OCT_F32, torch.float32, 2e-5), (OCT_BF16, torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("B,S,H,d", [(2, 77, 2, 32), (1, 300, 2, 64), (2, 512, 4, 64), (1, 1030, 3, 32)])
+def test_attention(compute, dtype, tol, B, S, H, d):
+    import math
+    g = torch.Generator().manual_seed(S)
+    qkv = torch.randn(B, S, 3 * H * d, generator=g).to(dtype)
+    dout = torch.randn(B, S, H * d, generator=g).to(dtype)
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.view(B, S, 3, H, d).unbind(2)
+    s = torch.einsum("bthd,bshd->bhts", q, k) / math.sqrt(d)
+    o_ref = torch.einsum("bhts,bshd->bthd", torch.softmax(s, -1), v).reshape(B, S, H * d)
+    (o_ref * dout.double()).sum().backward()
+    qd = qkv.to(DEV).requires_grad_(True)
+    out = ops.AttnFn.apply(qd, H, compute)
+    assert rel(out, o_ref.detach()) < tol
+    out.backward(dout.to(DEV))
+    assert rel(qd.grad, x.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("B,T,HW,E,u", [(2, 6, 64, 64, 3), (1, 12, 256, 1024, 3), (2, 3, 128, 264, 3)])
+def test_patch_embed_tc(B, T, HW, E, u):
+    g = torch.Generator().manual_seed(E)
+    imgs = torch.rand(B, 1, T, HW, HW, generator=g)
+    w, b = torch.randn(E, 1, u, 16, 16, generator=g) * 0.05, torch.randn(E, generator=g)
+    want = O.patch_embed(imgs.double(), w.double(), b.double()).reshape(B, -1, E)
+    out = ops.patch_embed_tc(imgs.to(DEV), w.view(E, -1).to(DEV).contiguous(), b.to(DEV), 16, u, torch.float32)
+    assert rel(out, want) < 2e-3  # tf32 operands (10-bit mantissa), fp32 accumulate
