@@ -1,9 +1,273 @@
-// placeholder until the tcgen05 flash kernels land
+// Flash-style self-attention on tcgen05 / TMEM (replaces flash_attn_qkvpacked_func, flash_attn/modules/mha.py:122-130:
+// non-causal, dropout 0, softmax scale d^-0.5; the pip package's sm_100 build is an mma.sync (HMMA) kernel).
+// qkv packed [B,S,3,H,d] bf16 is read in place through one 4-D TMA map (d, 3H, S, B).
+//
+// Forward: one CTA = 128 query rows of one (batch, head).  192 threads:
+//   warp 0   TMA producer: Q once, then K_j / V_j tiles through a ring
+//   warp 1   MMA issuer:   S_j = Q K_j^T (SS, both K-major) into one of two TMEM S buffers; O += P_j V_j (TS: P read
+//            from TMEM as the A operand, V^T taken from the same row-major smem tile through an MN-major descriptor)
+//   warps 2-5 softmax: thread <-> query row (TMEM lane), online softmax in the log2 domain with lazy rescaling
+//            (O is only rescaled when the running max grows by more than 2^8), P written back over S as bf16.
+// S_{j+1} is computed while the softmax of tile j runs.  head_dim 64 uses 128B swizzle, head_dim 32 uses 64B swizzle
+// (the TMA row pitch equals the inner box extent).
 #include "tc_common.cuh"
-int oct_attn_fwd_tc(const void*, void*, float*, int64_t, int64_t, int64_t, int64_t, float, cudaStream_t) {
-  oct_set_error("oct_attn_fwd(bf16): tcgen05 kernel not built"); return OCT_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int AT_BM = 128, AT_BN = 128, AT_THREADS = 192, AT_KV_STAGES = 4;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <int HD>
+struct AtCfg {
+  static constexpr int kRowBytes = HD * 2;                       // 64 or 128
+  static constexpr int kTileBytes = 128 * kRowBytes;             // one 128-row Q / K / V tile
+  static constexpr uint32_t kSwz = (HD == 64) ? tc::kSwz128 : tc::kSwz64;
+  static constexpr uint32_t kSBO = 8 * kRowBytes;                // 8-row swizzle atom
+  static constexpr int kSmem = kTileBytes * (1 + 2 * AT_KV_STAGES) + 1024 + 256;
+  static constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO = 256;
+};
+
+struct AtParams {
+  int S, H;
+  float scale_log2e;
+  __nv_bfloat16* out;  // [B,S,H,HD]
+  float* lse;          // [B,H,S]
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                    const AtParams p) {
+  using C = AtCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + C::kTileBytes;
+  uint8_t* sV = sK + AT_KV_STAGES * C::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_KV_STAGES * C::kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + AT_KV_STAGES;
+  uint64_t* s_full = kv_empty + AT_KV_STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;               // [2]
+  uint64_t* o_done = p_full + 2;               // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.S + AT_BN - 1) / AT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_qkv);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < AT_KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_full[s], 128); }
+    tc::mbar_init(o_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(q_full, C::kTileBytes);
+      tc::tma_load_4d(sQ, &tmap_qkv, q_full, 0, h, q0, b);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        tc::mbar_wait(&kv_empty[stage], phase ^ 1);
+        tc::mbar_arrive_expect_tx(&kv_full[stage], 2 * C::kTileBytes);
+        tc::tma_load_4d(sK + stage * C::kTileBytes, &tmap_qkv, &kv_full[stage], 0, p.H + h, j * AT_BN, b);
+        tc::tma_load_4d(sV + stage * C::kTileBytes, &tmap_qkv, &kv_full[stage], 0, 2 * p.H + h, j * AT_BN, b);
+        if (++stage == AT_KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, AT_BN);
+      constexpr uint32_t idesc_pv = tc::make_idesc(tc::kFmtBF16, false, true, AT_BM, HD);
+      const uint32_t q_addr = tc::smem_u32(sQ);
+      auto issue_qk = [&](int j, int stage) {
+        const uint32_t k_addr = tc::smem_u32(sK + stage * C::kTileBytes);
+        const uint32_t tmem_s = tmem_base + ((j & 1) ? C::kColS1 : C::kColS0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t da = tc::make_smem_desc(q_addr + k * 32, 16, C::kSBO, C::kSwz);
+          const uint64_t db = tc::make_smem_desc(k_addr + k * 32, 16, C::kSBO, C::kSwz);
+          tc::mma_ss(tmem_s, da, db, idesc_qk, k != 0);
+        }
+        tc::mma_commit(&s_full[j & 1]);
+      };
+      tc::mbar_wait(q_full, 0);
+      int stage = 0; uint32_t phase = 0;          // ring position of tile j
+      int nstage = 0; uint32_t nphase = 0;        // ring position of the next tile whose K has not been consumed yet
+      tc::mbar_wait(&kv_full[0], 0);
+      tc::tcgen05_fence_after();
+      issue_qk(0, 0);
+      if (++nstage == AT_KV_STAGES) { nstage = 0; nphase ^= 1; }
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {  // S_{j+1} = Q K_{j+1}^T overlaps softmax(j)
+          tc::mbar_wait(&kv_full[nstage], nphase);
+          tc::tcgen05_fence_after();
+          issue_qk(j + 1, nstage);
+          if (++nstage == AT_KV_STAGES) { nstage = 0; nphase ^= 1; }
+        }
+        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM, O rescaled if needed
+        tc::tcgen05_fence_after();
+        const uint32_t v_addr = tc::smem_u32(sV + stage * C::kTileBytes);
+        const uint32_t tmem_p = tmem_base + ((j & 1) ? C::kColS1 : C::kColS0);
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k) {
+          // V^T as an MN-major B operand: 16 kv rows per step; one MN chunk (= HD elements) so LBO is unused
+          const uint64_t db = tc::make_smem_desc(v_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
+          tc::mma_ts(tmem_base + C::kColO, tmem_p + k * 8, db, idesc_pv, (j | k) != 0);
+        }
+        tc::mma_commit(&kv_empty[stage]);
+        tc::mma_commit(o_done);
+        if (++stage == AT_KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+      (void)phase;
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t tmem_s = lane_addr + ((j & 1) ? C::kColS1 : C::kColS0);
+      tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc::tcgen05_fence_after();
+      uint32_t sr[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tc::tmem_ld_x32(tmem_s + c * 32, sr[c]);
+      tc::tmem_ld_wait();
+      const int valid = p.S - j * AT_BN;  // columns >= valid are out of range (TMA zero-filled K rows)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(sr[c][i]);
+          if (valid < AT_BN && c * 32 + i >= valid) { s = -INFINITY; sr[c][i] = __float_as_uint(s); }
+          mx = fmaxf(mx, s);
+        }
+      const float m_tile = mx * p.scale_log2e;
+      const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? m_tile : m;
+        if (j > 0) {
+          const float factor = need ? tc::fast_exp2(m - m_new) : 1.f;
+          tc::mbar_wait(o_done, (j - 1) & 1);  // O += P_{j-1} V_{j-1} has landed
+          tc::tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tc::tmem_ld_x32(lane_addr + C::kColO + c * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tc::tmem_st_x32(lane_addr + C::kColO + c * 32, o);
+          }
+          l *= factor;
+        }
+        m = m_new;
+      }
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = tc::fast_exp2(__uint_as_float(sr[c][2 * i]) * p.scale_log2e - m);
+          const float p1 = tc::fast_exp2(__uint_as_float(sr[c][2 * i + 1]) * p.scale_log2e - m);
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tc::tmem_st_x16(tmem_s + c * 16, pk);  // P (bf16 pairs) overwrites the first 64 columns of this S buffer
+      }
+      l += lsum;
+      tc::tmem_st_wait();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&p_full[j & 1]);
+    }
+    // epilogue: O / l -> bf16, lse
+    tc::mbar_wait(o_done, (n_kv - 1) & 1);
+    tc::tcgen05_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = p.out + (((size_t)b * p.S + qi) * p.H + h) * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld_x32(lane_addr + C::kColO + c * 32, o);
+      tc::tmem_ld_wait();
+      if (qi < p.S) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) = v;
+        }
+      }
+    }
+    if (qi < p.S) p.lse[((size_t)b * p.H + h) * p.S + qi] = (m + log2f(l)) * kLn2;
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
 }
-int oct_attn_bwd_tc(const void*, const void*, const void*, const float*, void*, void*, size_t, int64_t, int64_t, int64_t, int64_t, float, cudaStream_t) {
-  oct_set_error("oct_attn_bwd(bf16): tcgen05 kernel not built"); return OCT_ERR_UNSUPPORTED;
+
+int make_qkv_map(CUtensorMap* map, const void* qkv, int64_t B, int64_t S, int64_t H, int64_t d, uint32_t box_rows,
+                 const char* who) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)3 * H * d * 2, (uint64_t)S * 3 * H * d * 2};
+  uint32_t box[4] = {(uint32_t)d, 1, box_rows, 1};
+  return oct_make_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, qkv, dims, str, box, who,
+                       d == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
-size_t oct_attn_bwd_tc_ws_bytes(int64_t B, int64_t S, int64_t H, int64_t d) { return (size_t)B * H * S * sizeof(float); }
+
+template <int HD>
+int launch_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H, float scale, cudaStream_t st) {
+  using C = AtCfg<HD>;
+  CUtensorMap map;
+  int rc = make_qkv_map(&map, qkv, B, S, H, HD, 128, "oct_attn_fwd(bf16)");
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) { oct_set_error("oct_attn_fwd(bf16): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  AtParams p;
+  p.S = (int)S; p.H = (int)H; p.scale_log2e = scale * kLog2e; p.out = (__nv_bfloat16*)out; p.lse = lse;
+  dim3 grid((unsigned)ceil_div64(S, AT_BM), (unsigned)H, (unsigned)B);
+  attn_fwd_tc_kernel<HD><<<grid, AT_THREADS, C::kSmem, st>>>(map, p);
+  return oct_check_launch("oct_attn_fwd(bf16)");
+}
+
+}  // namespace
+
+int oct_attn_fwd_tc(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H, int64_t d, float scale,
+                    cudaStream_t st) {
+  OCT_REQUIRE(aligned16(qkv) && aligned16(out), "oct_attn_fwd(bf16): pointers must be 16-byte aligned");
+  OCT_REQUIRE(S < (1 << 24), "oct_attn_fwd(bf16): S too large");
+  if (d == 64) return launch_fwd<64>(qkv, out, lse, B, S, H, scale, st);
+  if (d == 32) return launch_fwd<32>(qkv, out, lse, B, S, H, scale, st);
+  oct_set_error("oct_attn_fwd(bf16): head dim %lld unsupported by the tcgen05 kernel (32 or 64)", (long long)d);
+  return OCT_ERR_UNSUPPORTED;
+}
+
+// ---- backward: see attn_bwd_tc.cu ----

@@ -31,7 +31,7 @@ oct_encode_tiled_fn oct_get_encode_tiled() {
 }
 
 int oct_make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box, const char* who) {
+                  const uint64_t* strides_bytes, const uint32_t* box, const char* who, CUtensorMapSwizzle swizzle) {
   oct_encode_tiled_fn enc = oct_get_encode_tiled();
   if (!enc) return OCT_ERR_UNSUPPORTED;
   cuuint64_t gdim[5], gstr[4];
@@ -39,7 +39,7 @@ int oct_make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     oct_set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d; base %p dims %llu,%llu stride %llu box %u,%u)", who,

@@ -63,11 +63,11 @@ __global__ void __launch_bounds__(kSortThreads) mask_sort_kernel(const float* __
 
 extern "C" int oct_mask_sort(const float* noise, int64_t B, int64_t L, int64_t keep, int64_t* ids_restore,
                              int64_t* ids_keep, float* mask, oct_stream_t stream) {
-  OCT_REQUIRE(noise && ids_restore && mask, "oct_mask_sort: null pointer");
   OCT_REQUIRE(B >= 0 && L >= 0 && keep >= 0 && keep <= L, "oct_mask_sort: bad sizes B=%lld L=%lld keep=%lld",
               (long long)B, (long long)L, (long long)keep);
+  OCT_REQUIRE(B == 0 || L == 0 || (noise && ids_restore && mask), "oct_mask_sort: null pointer");
   OCT_REQUIRE(L <= 16384, "oct_mask_sort: L=%lld > 16384 unsupported", (long long)L);
-  OCT_REQUIRE(keep == 0 || ids_keep, "oct_mask_sort: ids_keep is null");
+  OCT_REQUIRE(B == 0 || keep == 0 || ids_keep, "oct_mask_sort: ids_keep is null");
   OCT_REQUIRE(B <= 65535, "oct_mask_sort: B too large");
   if (B == 0 || L == 0) return OCT_OK;
   dim3 grid((unsigned)ceil_div64(L, kSortThreads), (unsigned)B);

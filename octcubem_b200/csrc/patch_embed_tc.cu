@@ -1,6 +1,7 @@
 // PatchEmbed.forward (custom_util/video_vit.py:74-83): Conv3d(1 -> E, kernel = stride = (u,16,16)) + flatten +
 // 'ncts->ntsc', as an im2col-free GEMM.  The fp32 volume is never re-laid out: a 5-D TMA box (kw, kh, w, h, frame)
-// drops 128 tokens x 32 k-elements straight into a 128B-swizzled K-major smem tile, tcgen05.mma kind::tf32 contracts it
+// drops 128 tokens x 16 k-elements (one patch row: 64 contiguous bytes, hence the 64B swizzle mode — the TMA row
+// pitch in smem equals the inner box extent) into a K-major smem tile, tcgen05.mma kind::tf32 contracts it
 // against the fp32 Conv3d weight viewed as [E, u*16*16] (vv:69-72 weight order == patchify order), the
 // accumulator lives in TMEM, and the epilogue adds the bias and writes token-major [B, T'*h*w, E] directly.
 //
@@ -10,9 +11,10 @@
 
 namespace {
 
-constexpr int PE_BLOCK_M = 128, PE_BLOCK_N = 256, PE_BLOCK_K = 32 /* fp32 elements = 128 B */, PE_UMMA_K = 8;
-constexpr int PE_STAGES = 2;
-constexpr int PE_A_BYTES = PE_BLOCK_M * 128, PE_B_BYTES = PE_BLOCK_N * 128;
+constexpr int PE_BLOCK_M = 128, PE_BLOCK_N = 256, PE_BLOCK_K = 16 /* fp32 elements = 64 B */, PE_UMMA_K = 8;
+constexpr int PE_STAGES = 4;
+constexpr int PE_ROW_BYTES = PE_BLOCK_K * 4;
+constexpr int PE_A_BYTES = PE_BLOCK_M * PE_ROW_BYTES, PE_B_BYTES = PE_BLOCK_N * PE_ROW_BYTES;
 constexpr int PE_STAGE_BYTES = PE_A_BYTES + PE_B_BYTES;
 constexpr int PE_SMEM = PE_STAGES * PE_STAGE_BYTES + 1024 + 128;
 constexpr int PE_THREADS = 192;
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(PE_THREADS, 2) patch_embed_tc_kernel(const __g
   const int tp = m_tile % p.Tp;
   const int b = m_tile / p.Tp;
   const int n0 = blockIdx.y * PE_BLOCK_N;
-  const int num_kb = p.u * 8;  // u * (16 kh / 2)
+  const int num_kb = p.u * 16;  // one (kt, kh) patch row of 16 pixels per k-block
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_x);
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(PE_THREADS, 2) patch_embed_tc_kernel(const __g
       for (int kb = 0; kb < num_kb; ++kb) {
         tc::mbar_wait(&empty_bar[stage], phase ^ 1);
         tc::mbar_arrive_expect_tx(&full_bar[stage], PE_STAGE_BYTES);
-        const int kt = kb >> 3, kh0 = (kb & 7) * 2;
+        const int kt = kb >> 4, kh0 = kb & 15;
         tc::tma_load_5d(smem_a + stage * PE_A_BYTES, &tmap_x, &full_bar[stage], 0, kh0, wt * 16, ht * 8,
                         b * p.T + tp * p.u + kt);
         tc::tma_load_2d(smem_b + stage * PE_B_BYTES, &tmap_w, &full_bar[stage], kb * PE_BLOCK_K, n0);
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(PE_THREADS, 2) patch_embed_tc_kernel(const __g
         const uint32_t b_addr = tc::smem_u32(smem_b + stage * PE_B_BYTES);
 #pragma unroll
         for (int k = 0; k < PE_BLOCK_K / PE_UMMA_K; ++k) {
-          const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t db = tc::make_smem_desc(b_addr + k * 32, 16, 1024);
+          const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, 8 * PE_ROW_BYTES, tc::kSwz64);
+          const uint64_t db = tc::make_smem_desc(b_addr + k * 32, 16, 8 * PE_ROW_BYTES, tc::kSwz64);
           tc::mma_ss_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
         }
         tc::mma_commit(&empty_bar[stage]);
@@ -165,15 +167,17 @@ extern "C" int oct_patch_embed_fwd(const float* imgs, const float* weight, const
   {
     uint64_t dims[5] = {16, 16, (uint64_t)wp, (uint64_t)hp, (uint64_t)(B * T)};
     uint64_t str[4] = {(uint64_t)W * 4, 64, (uint64_t)16 * W * 4, (uint64_t)H * W * 4};
-    uint32_t box[5] = {16, 2, 16, 8, 1};
-    int rc = oct_make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, imgs, dims, str, box, "oct_patch_embed_fwd(volume)");
+    uint32_t box[5] = {16, 1, 16, 8, 1};
+    int rc = oct_make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, imgs, dims, str, box, "oct_patch_embed_fwd(volume)",
+                           CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)E};
     uint64_t str[1] = {(uint64_t)K * 4};
     uint32_t box[2] = {PE_BLOCK_K, PE_BLOCK_N};
-    int rc = oct_make_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, weight, dims, str, box, "oct_patch_embed_fwd(weight)");
+    int rc = oct_make_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, weight, dims, str, box, "oct_patch_embed_fwd(weight)",
+                           CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   PeParams prm;

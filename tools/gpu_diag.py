@@ -153,6 +153,31 @@ def t_patch_embed():
             return
 
 
+def t_pe_probe():
+    """One-hot weights: out[tok, e] must equal patch element e of token tok.  Three probes (x, y, frame coordinates)
+    decode which input element every output actually reads."""
+    B, T, HW, u = 1, 3, 64, 3
+    E = 768
+    w = torch.eye(768).view(E, 1, 3, 16, 16).contiguous()
+    bias = torch.zeros(E)
+    f, y, x = torch.meshgrid(torch.arange(T), torch.arange(HW), torch.arange(HW), indexing="ij")
+    for name, vol in (("x", x), ("y", y), ("f", f)):
+        imgs = vol.float().view(1, 1, T, HW, HW).contiguous()
+        out = ops.patch_embed_tc(imgs.to(dev), w.view(E, -1).to(dev).contiguous(), bias.to(dev), 16, u, torch.float32).cpu()
+        want = torch.nn.functional.conv3d(imgs, w, bias, stride=(u, 16, 16)).flatten(2).transpose(1, 2)
+        print(f"probe {name}: rel {rel(out, want):.3e}")
+        for tok in (0, 1, 5):
+            print(f"   tok {tok} got  e[0:40]  ", out[0, tok, :40].int().tolist())
+            print(f"   tok {tok} want e[0:40]  ", want[0, tok, :40].int().tolist())
+            print(f"   tok {tok} got  e[256:272]", out[0, tok, 256:272].int().tolist(), " want", want[0, tok, 256:272].int().tolist())
+    # B probe: constant image = 1 -> out[tok, e] = sum_k W[e, k]; use W[e, k] = (k == e % 768) * (e + 1)
+    imgs = torch.ones(1, 1, T, HW, HW)
+    w2 = torch.zeros(E, 768)
+    w2[torch.arange(E), torch.arange(E)] = torch.arange(1, E + 1).float()
+    out = ops.patch_embed_tc(imgs.to(dev), w2.to(dev).contiguous(), bias.to(dev), 16, u, torch.float32).cpu()
+    print("probe B: got e[0:24]", out[0, 0, :24].int().tolist(), "... e[760:768]", out[0, 0, 760:].int().tolist())
+
+
 def t_timing():
     """Rough single-kernel timings (L2-warm) for orientation only."""
     def timeit(fn, n=20):
@@ -192,6 +217,7 @@ TESTS = {
     "attn_simt_bf16": lambda: t_attn(OCT_SIMT_BF16, torch.bfloat16, 8e-3),
     "attn_tc": lambda: t_attn(OCT_BF16, torch.bfloat16, 8e-3, cases=((2, 77, 2, 32), (1, 300, 2, 64), (2, 512, 4, 64), (1, 1030, 3, 32))),
     "patch_embed": t_patch_embed,
+    "pe_probe": t_pe_probe,
     "timing": t_timing,
 }
 
