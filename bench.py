@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — 3D-MAE pre-training step throughput (volumes/s) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm's CPU path on this box's host cores
+
+Workload (BASELINE.json configs[1]): MaskedAutoencoderViT ViT-L encoder / 512x8x16 decoder, patch 16, t_patch 3,
+48x256x256 single-channel volumes, mask 0.9, bf16 forward+backward, batch 8 per GPU, synthetic volumes, random-init
+weights.  A "step" = forward + backward (+ gradient all-reduce over NCCL when N > 1); the optimizer step is NOT part of
+the hot path and is reported separately (`optimizer_ms`, torch fused AdamW, informational).
+Prints ONE JSON line (see the README / DESIGN.md §Measurement for the fields).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES, IMG, BATCH, MASK = 48, 256, 8, 0.9
+# algorithmic FLOPs per volume, fwd+bwd: 2MNK per GEMM, 4 S^2 dim per attention layer, bwd = 2x fwd
+GF_PER_VOLUME = {48: 2260.0, 60: 3097.0}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (recipe of B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference algorithm's CPU path (models_mae.py-style non-flash blocks, fp32)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn():
+    """Returns (fn, description): fn() runs forward+backward of ONE 48x256x256 volume through oracle.cpu_baseline_forward
+    (the restatement of the reference class with use_flash_attn=False, pinned against the reference in tests/)."""
+    from oracle import mae3d_oracle as O
+    cfg = O.MAEConfig(num_frames=FRAMES, pred_t_dim=FRAMES)
+    torch.manual_seed(0)
+    sd = {k: v.requires_grad_(True) for k, v in O.init_state_dict(cfg, seed=0).items()}
+    vol = O.synthetic_volume(1, FRAMES, IMG, IMG, seed=0)
+    noise = O.synthetic_noise(1, cfg.t_grid * cfg.grid ** 2, seed=1)
+
+    def fn():
+        for v in sd.values():
+            v.grad = None
+        loss, _, _ = O.cpu_baseline_forward(cfg, sd, vol, MASK, noise)
+        loss.backward()
+        return float(loss.detach())
+
+    return fn, "1 volume (of the batch-8 workload) forward+backward, fp32, torch CPU kernels"
+
+
+def run_cpu(max_steps, warmup, budget_s):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn, sample = cpu_reference_step_fn()
+    t0 = time.time()
+    fn()                                   # first call doubles as warm-up (allocator, thread pool)
+    first = time.time() - t0
+    times = []
+    if first * 2 < budget_s:               # room for at least one more: discard the warm-up call
+        for _ in range(max(0, min(warmup, 1) - 1)):
+            fn()
+        while len(times) < max_steps and (time.time() - t0) + (times[-1] if times else first) < budget_s:
+            t1 = time.time(); fn(); times.append(time.time() - t1)
+    if not times:
+        times = [first]
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": 1.0 / med, "unit": "volumes/s", "cores": cores, "kind": "port",
+            "sample": f"{sample}; {len(times)} timed run(s), median {med:.2f} s/volume", "steps_run": len(times),
+            "ms_per_step": med * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_cpu(args.steps, args.warmup, budget_s=150.0)
+    line = {"metric": "3D-MAE pretrain volumes/sec", "value": r["value"], "unit": "volumes/s", "n_gpus": args.gpus,
+            "steps": r["steps_run"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": workload_name(), "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "volumes/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name():
+    return (f"3D MAE ViT-L/16 t_patch 3 + dec 512x8x16, {FRAMES}x{IMG}x{IMG} volumes, mask {MASK}, bf16 fwd+bwd, "
+            f"batch {BATCH}/GPU (BASELINE.json configs[1])")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch.distributed as dist
+    from octcubem_b200 import _lib, models_mae, ops
+    from octcubem_b200.dp import GradReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    pk = peaks()
+
+    torch.manual_seed(1234)
+    model = models_mae.flash_attn_mae_vit_large_patch16(
+        input_size=IMG, in_chans=1, num_frames=FRAMES, t_patch_size=3, pred_t_dim=FRAMES, sep_pos_embed=True,
+        cls_embed=True, high_res_input_size=512, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16,
+        precision="bf16").to(dev)
+    if world > 1:  # same weights on every rank (DDP broadcasts rank 0's at construction)
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    reducer = GradReducer(model) if world > 1 else None
+    L = (FRAMES // 3) * (IMG // 16) ** 2
+
+    g = torch.Generator().manual_seed(100 + rank)
+    host_vol = torch.rand(BATCH, 1, FRAMES, IMG, IMG, generator=g)
+    host_vol[:, :, :3] = 0; host_vol[:, :, -3:] = 0           # centre-padding of PatientDataset_inhouse.py:439-444
+    host_vol = host_vol.pin_memory()
+    vol = host_vol.to(dev)
+    loss_out = torch.zeros((), device=dev)
+
+    def step(v):
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            model.zero_grad(set_to_none=True)
+        loss, _, _ = model(v, mask_ratio=MASK)                  # noise drawn on device, like models...:350
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        loss_out.copy_(loss.detach())
+
+    # eager warm-up (also: TMA maps / func attributes / reducer bucket discovery), launch count of one step
+    for _ in range(2):
+        step(vol)
+    torch.cuda.synchronize()
+    c0 = lib.oct_launch_count()
+    step(vol)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.oct_launch_count() - c0)
+
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(vol)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step(vol)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    run = (lambda: graph.replay()) if graph is not None else (lambda: step(vol))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        run()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(run, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * BATCH / (ms_step / 1e3)
+
+    # end to end through the public API: pinned host volume -> device, step, loss -> host, every step
+    def e2e_step():
+        vol.copy_(host_vol, non_blocking=True)
+        run()
+        return loss_out.item()
+
+    for _ in range(3):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * BATCH / (e2e_ms / 1e3)
+    last_loss = float(loss_out)
+
+    # roofline of the dominant kernel, timed alone at its in-step shape (CUDA events on the launching stream)
+    roof = dominant_kernel_roofline(ops, dev, pk)
+
+    # optimizer step, informational (not on the hot path)
+    opt_ms = None
+    try:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+        for _ in range(2):
+            opt.step()
+        opt_ms = timed(opt.step, 5) / 5
+    except Exception:
+        pass
+
+    if rank == 0:
+        gf = GF_PER_VOLUME[FRAMES]
+        line = {
+            "metric": "3D-MAE pretrain volumes/sec", "value": value, "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(), "global_batch": world * BATCH, "parallelism": f"dp{world}",
+                       "step": "forward + backward" + (" + NCCL gradient all-reduce overlapped with backward" if world > 1 else "")
+                               + "; optimizer excluded (SURVEY §8d), see optimizer_ms",
+                       "cuda_graph": graph is not None,
+                       "l2": "per-step working set (1.3 GB fp32 weights + bf16 shadows + ~10 GB activations) >> 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "volumes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": host_vol.numel() * 4 * 1,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "step_tflops_per_gpu": gf * BATCH / ms_step,
+            "step_frac_of_bf16_sustained": gf * BATCH / ms_step / pk["bf16_sustained"],
+            "roofline": roof,
+            "optimizer_ms": opt_ms,
+            "loss": last_loss,
+            "peaks": pk["src"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_cpu(1, 0, budget_s=60.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "volumes/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(ops, dev, pk):
+    """Decoder attention backward (B=8, S=4097, 16 heads x 32): the largest single share of the step (profiles/)."""
+    from octcubem_b200._lib import OCT_BF16
+    B, S, H, d = BATCH, (FRAMES // 3) * 256 + 1, 16, 32
+    qkv = (torch.randn(B, S, 3 * H * d, device=dev) * 0.5).bfloat16()
+    dout = torch.randn(B, S, H * d, device=dev).bfloat16()
+    out, lse = ops.attn_fwd(qkv, H, d, OCT_BF16)
+    for _ in range(3):
+        ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16)
+    torch.cuda.synchronize()
+    n = 10
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / n
+    flops = 2.0 * 4.0 * S * S * (H * d) * B        # bwd = 2 x fwd, fwd = 4 S^2 dim per layer
+    achieved = flops / ms / 1e9
+    return {"kernel": "attn_bwd_tc_kernel<32> (+delta, dq-convert) decoder shape B8 S4097 H16 d32", "bound": "tensor",
+            "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"],
+            "traffic": None, "ms_per_launch": ms, "peak_source": pk["src"],
+            "note": "algorithmic FLOPs (no recompute counted); inputs 100 MB qkv + 33 MB dout > L2 is not exceeded by much"}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

@@ -49,6 +49,8 @@ enum { OCT_EPI_NONE = 0, OCT_EPI_BIAS = 1, OCT_EPI_BIAS_GELU = 2, OCT_EPI_DGELU 
 
 const char* oct_version(void);
 const char* oct_last_error(void);
+/* number of kernels this library has launched in this process so far (evidence for bench.py's gpu_launches) */
+uint64_t oct_launch_count(void);
 /* sm_count / compute capability of the current device; returns OCT_ERR_UNSUPPORTED unless cc == 10.x */
 int oct_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -22,6 +22,7 @@ P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 SIGNATURES = {
     "oct_version": (c_char_p, []),
     "oct_last_error": (c_char_p, []),
+    "oct_launch_count": (ctypes.c_uint64, []),
     "oct_device_info": (I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "oct_mask_sort": (I, [P, L, L, L, P, P, P, P]),
     "oct_patchify": (I, [P, P, I, P, P, L, L, L, L, L, L, L, L, P]),

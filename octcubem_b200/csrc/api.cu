@@ -11,7 +11,10 @@ void oct_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;  // kernels launched through this library (bench.py reports it)
+
 int oct_check_launch(const char* what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     oct_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -33,6 +36,7 @@ int oct_num_sms() {
   return cached;
 }
 
+extern "C" uint64_t oct_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* oct_version(void) { return "octcube_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* oct_last_error(void) { return g_err; }
 

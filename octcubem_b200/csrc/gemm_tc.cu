@@ -80,6 +80,8 @@ struct GemmParams {
   const float* bias;
   void* aux;
   int beta;
+  int splits;        // split-K factor (fp32 D, EPI_NONE only): partial products are reduced with red.global.add
+  int kb_per_split;  // k-blocks per split
 };
 
 template <bool A_MN, bool B_MN, int BLOCK_N>
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M, num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_work = num_tiles * p.splits;  // work item w: tile = w % num_tiles, split = w / num_tiles
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -135,11 +138,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(t, m_blk, n_blk);
+        tile_coords(w % num_tiles, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (w / num_tiles) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           tc::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           uint8_t* sa = smem_a + stage * C::kABytes;
@@ -170,11 +174,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       if (lane == 0) {
         tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const int num_kb = min(num_kb_total, (w / num_tiles + 1) * p.kb_per_split) - (w / num_tiles) * p.kb_per_split;
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tcgen05_fence_after();
@@ -202,9 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(t, m_blk, n_blk);
+      tile_coords(w % num_tiles, m_blk, n_blk);
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
       const int n0 = n_blk * BLOCK_N;
       tc::mbar_wait(&tmem_full[acc], acc_phase);
@@ -274,6 +279,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 } else if (p.epilogue == OCT_EPI_DGELU) {
                   const float4 a = *reinterpret_cast<const float4*>(ax + i);
                   o.x *= gelu_erf_grad(a.x); o.y *= gelu_erf_grad(a.y); o.z *= gelu_erf_grad(a.z); o.w *= gelu_erf_grad(a.w);
+                } else if (p.splits > 1) {  // split-K partial: reduce in L2 (D was zeroed, or holds beta*D)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + i), "f"(o.x), "f"(o.y),
+                               "f"(o.z), "f"(o.w) : "memory");
+                  continue;
                 } else if (p.beta) {
                   const float4 a = *reinterpret_cast<const float4*>(d + i);
                   o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
@@ -309,7 +318,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
     attr_done = true;
   }
   const int num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = num_tiles < oct_num_sms() ? num_tiles : oct_num_sms();
+  const int num_work = num_tiles * p.splits;
+  const int grid = num_work < oct_num_sms() ? num_work : oct_num_sms();
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, p);
   return oct_check_launch("oct_gemm(bf16)");
 }
@@ -352,6 +362,26 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   GemmParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.ldd = ldd; p.D = D; p.d_bf16 = (d_dtype == OCT_BF16);
   p.epilogue = epilogue; p.bias = bias; p.aux = aux; p.beta = beta;
+  // split-K: wgrad-shaped problems (few output tiles, long contraction) would otherwise occupy a fraction of the chip
+  p.splits = 1;
+  const int num_kb = (int)ceil_div64(K, BLOCK_K);
+  p.kb_per_split = num_kb;
+  if (d_dtype == OCT_F32 && epilogue == OCT_EPI_NONE) {
+    const int64_t tiles = ceil_div64(M, BLOCK_M) * ceil_div64(N, block_n);
+    const int sms = oct_num_sms();
+    if (tiles * 2 <= sms && num_kb >= 16) {
+      int splits = (int)(sms / tiles);
+      if (splits > num_kb / 8) splits = num_kb / 8;  // keep >= 8 k-blocks (512 of K) per split
+      if (splits > 1) {
+        p.kb_per_split = (num_kb + splits - 1) / splits;
+        p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+        if (!beta) {
+          cudaError_t e = cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st);
+          if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+      }
+    }
+  }
 #define GO(AMN, BMN)                                                                    \
   return block_n == 256 ? launch<AMN, BMN, 256>(ta, tb, p, st) : launch<AMN, BMN, 128>(ta, tb, p, st)
   switch (layout) {

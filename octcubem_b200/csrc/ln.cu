@@ -199,13 +199,22 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const TDY* __
   }
 }
 
-__global__ void ln_bwd_finish_kernel(const float* __restrict__ ws, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int nblocks, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * C) return;
+// 32 columns x 32 row-slices per CTA; fixed summation order (slice-strided partials, then slices 0..31)
+__global__ void __launch_bounds__(1024) ln_bwd_finish_kernel(const float* __restrict__ ws, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int nblocks, int C) {
+  __shared__ float sm[32][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
-  for (int b = 0; b < nblocks; ++b) a += ws[(size_t)b * 2 * C + i];
-  if (i < C) dgamma[i] = a; else dbeta[i - C] = a;
+  if (i < 2 * C)
+    for (int b = threadIdx.y; b < nblocks; b += 32) a += ws[(size_t)b * 2 * C + i];
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+    if (i < C) dgamma[i] = t; else dbeta[i - C] = t;
+  }
 }
 
 static int64_t ln_bwd_blocks(int64_t M) {
@@ -233,7 +242,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* mean, const
                                                      (TLP*)dx_lp, ws, M, C);
   int rc = oct_check_launch("oct_add_ln_bwd");
   if (rc) return rc;
-  ln_bwd_finish_kernel<<<(unsigned)ceil_div64(2 * C, 256), 256, 0, st>>>(ws, dgamma, dbeta, (int)blocks, C);
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div64(2 * C, 32), dim3(32, 32), 0, st>>>(ws, dgamma, dbeta, (int)blocks, C);
   return oct_check_launch("oct_add_ln_bwd(finish)");
 }
 

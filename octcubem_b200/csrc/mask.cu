@@ -194,40 +194,78 @@ __global__ void gather_tokens_bwd_copy_kernel(const float* __restrict__ dout, TD
     Vec4<TD>::st(dst + c, *reinterpret_cast<const float4*>(src + c));
 }
 
-// backward part 2: deterministic segmented sums.  CTA x in [0,G): spatial slot x ; [G, G+Tp): temporal slot ; last: cls.
-// Every CTA scans the B*keep kept ids in order and accumulates the matching rows (fixed order => reproducible).
+// backward part 2: deterministic segmented sums.  CTA x in [0,Gs): spatial slot x ; [Gs, Gs+Tp): temporal slot ; last: cls.
+// Each CTA first collects the kept tokens that fall into its slot (parallel scan of the B*keep ids into a shared list),
+// orders that short list by flat index, then accumulates the matching rows in that fixed order (reproducible sums).
+constexpr int kPosMaxList = 2048;
 __global__ void gather_tokens_bwd_pos_kernel(const float* __restrict__ dout, const int64_t* __restrict__ ids_keep,
                                              float* __restrict__ d_pos_sp, float* __restrict__ d_pos_tmp,
                                              float* __restrict__ d_cls_row, int B, int keep, int G, int Gs, int Tp,
                                              int C, int has_cls) {
+  __shared__ int s_list[kPosMaxList];
+  __shared__ int s_sorted[kPosMaxList];
+  __shared__ int s_count;
   const int slot = blockIdx.x;
   const int rows = keep + has_cls;
-  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-  if (c >= C) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (slot == Gs + Tp) {  // cls
-    for (int b = 0; b < B; ++b) {
-      float4 v = *reinterpret_cast<const float4*>(dout + (size_t)b * rows * C + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = 0; b < B; ++b) {
+        float4 v = *reinterpret_cast<const float4*>(dout + (size_t)b * rows * C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(d_cls_row + c) = acc;
     }
-    *reinterpret_cast<float4*>(d_cls_row + c) = acc;
     return;
   }
   const bool spatial = slot < Gs;
   const int want = spatial ? slot : slot - Gs;
-  for (int b = 0; b < B; ++b) {
-    const int64_t* ids = ids_keep + (size_t)b * keep;
-    for (int i = 0; i < keep; ++i) {
-      const int tok = (int)ids[i];  // uniform across the CTA -> broadcast load
+  // each thread owns up to 4 float4 column chunks (C <= 4 * 4 * blockDim.x, checked by the host)
+  float4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int total = B * keep;
+  // flat-index segments of at most kPosMaxList ids: a segment's matches always fit the shared list, and processing
+  // segments in increasing order keeps the global summation order = increasing flat index
+  for (int seg = 0; seg < total; seg += kPosMaxList) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int seg_end = min(total, seg + kPosMaxList);
+    for (int f = seg + threadIdx.x; f < seg_end; f += blockDim.x) {
+      const int tok = (int)ids_keep[f];
       const int key = spatial ? (tok % G) : (tok / G);
-      if (key == want) {
-        float4 v = *reinterpret_cast<const float4*>(dout + ((size_t)b * rows + i + has_cls) * C + c);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (key == want) s_list[atomicAdd(&s_count, 1)] = f;
+    }
+    __syncthreads();
+    const int n = s_count;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort (flat indices are unique)
+      const int v = s_list[i];
+      int r = 0;
+      for (int j = 0; j < n; ++j) r += (s_list[j] < v);
+      s_sorted[r] = v;
+    }
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+      const int f = s_sorted[i];
+      const int b = f / keep, r = f - b * keep;
+      const float* src = dout + ((size_t)b * rows + r + has_cls) * C;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = (threadIdx.x + k * blockDim.x) * 4;
+        if (c < C) {
+          const float4 v = *reinterpret_cast<const float4*>(src + c);
+          acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+        }
       }
     }
   }
-  float* dst = spatial ? (d_pos_sp + (size_t)want * C + c) : (d_pos_tmp + (size_t)want * C + c);
-  *reinterpret_cast<float4*>(dst) = acc;
+  float* dst = spatial ? (d_pos_sp + (size_t)want * C) : (d_pos_tmp + (size_t)want * C);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = (threadIdx.x + k * blockDim.x) * 4;
+    if (c < C) *reinterpret_cast<float4*>(dst + c) = acc[k];
+  }
 }
 
 extern "C" int oct_gather_tokens_bwd(const float* dout, const int64_t* ids_keep, void* dx_keep, int dx_dtype,
@@ -255,7 +293,8 @@ extern "C" int oct_gather_tokens_bwd(const float* dout, const int64_t* ids_keep,
   }
   const int Gs = d_pos_sp ? (int)G : 0;  // no spatial slots when the caller has no pos tables (plain random_masking)
   if (Gs + Tp + has_cls == 0) return OCT_OK;
-  dim3 grid2((unsigned)(Gs + Tp + has_cls), (unsigned)ceil_div64(C / 4, threads));
+  OCT_REQUIRE(C <= 16 * threads, "oct_gather_tokens_bwd: C too large");
+  dim3 grid2((unsigned)(Gs + Tp + has_cls), 1);
   // slot numbering inside the kernel: [0,Gs) spatial, [Gs,Gs+Tp) temporal, Gs+Tp cls
   gather_tokens_bwd_pos_kernel<<<grid2, threads, 0, st>>>(dout, ids_keep, d_pos_sp, d_pos_tmp, d_cls_row, (int)B,
                                                           (int)keep, (int)G, Gs, Tp, (int)C, has_cls);

@@ -1,0 +1,161 @@
+"""Data-parallel gradient reducer: replaces torch.nn.parallel.DistributedDataParallel at the reference's call site
+(Pre-training/main_pretrain_oph_joint_2d512_flash_attn.py:435-439, init custom_util/misc.py:252-297).
+
+DDP semantics are kept: every rank computes its local masked-mean loss, gradients are summed over ranks
+and divided by the world size.  Mechanics are B200-first rather than DDP's:
+  * buckets are laid out in BACKWARD order (decoder first, patch-embed / pos tables last) so that the only exposed
+    communication is the small final bucket;
+  * each parameter's gradient is moved into its flat fp32 bucket by a post-accumulate hook, `param.grad` becomes a
+    view of the bucket (no second copy after the collective);
+  * a bucket is all-reduced on a dedicated side stream the moment its last gradient lands — NCCL over NVLink 5 /
+    NVSwitch runs underneath the remaining backward kernels; `finish()` joins the streams;
+  * parameters that take no part in the step (the two high-res patch-embed tensors on a 3D-only step, quirk Q13) are
+    discovered on the first, non-overlapped, step and left out of the buckets.
+Works on CPU tensors with the gloo backend (used by the world_size-2 tests) — there the "side stream" is implicit.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter], names: List[str], device, dtype):
+        self.params, self.names = params, names
+        self.numel = sum(p.numel() for p in params)
+        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)
+        self.views = []
+        off = 0
+        for p in params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.pending = len(params)
+        self.work = None
+
+
+class GradReducer:
+    def __init__(self, model: torch.nn.Module, process_group=None, bucket_mb: float = 32.0, first_bucket_mb: float = 8.0,
+                 last_bucket_mb: float = 4.0):
+        self.model = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.bucket_bytes = int(bucket_mb * 2 ** 20)
+        self.first_bucket_bytes = int(first_bucket_mb * 2 ** 20)
+        self.last_bucket_bytes = int(last_bucket_mb * 2 ** 20)
+        self.buckets: Optional[List[_Bucket]] = None
+        self._slot: Dict[int, tuple] = {}
+        self._hooks = []
+        self._order: List[str] = []   # order in which gradients became ready on the discovery step
+        self._named = dict(model.named_parameters())
+        self._discovering = True
+        dev = next(model.parameters()).device
+        self.device = dev
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        for name, p in self._named.items():
+            if p.requires_grad:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(name)))
+
+    # ------------------------------------------------------------------ bucket construction
+    def _build(self, ready_order: List[str]):
+        """ready_order: parameter names in the order their gradients appeared (backward order)."""
+        sizes = [self._named[n].numel() * 4 for n in ready_order]
+        # the tail bucket = the last-ready parameters, at most last_bucket_bytes: the only exposed communication
+        tail_start, acc = len(ready_order), 0
+        while tail_start > 0 and (acc + sizes[tail_start - 1] <= self.last_bucket_bytes or tail_start == len(ready_order)):
+            tail_start -= 1
+            acc += sizes[tail_start]
+        groups, cur, cur_bytes = [], [], 0
+        for i in range(tail_start):
+            limit = self.first_bucket_bytes if not groups else self.bucket_bytes  # small first bucket starts the pipe early
+            if cur and cur_bytes + sizes[i] > limit:
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(ready_order[i])
+            cur_bytes += sizes[i]
+        if cur:
+            groups.append(cur)
+        if tail_start < len(ready_order):
+            groups.append(list(ready_order[tail_start:]))
+        buckets = [_Bucket([self._named[n] for n in g], g, self.device, torch.float32) for g in groups]
+        self.buckets = buckets
+        self._slot = {}
+        for bi, b in enumerate(buckets):
+            for pi, p in enumerate(b.params):
+                self._slot[id(p)] = (bi, pi)
+
+    def bucket_layout(self):
+        return [(b.names, b.numel) for b in (self.buckets or [])]
+
+    # ------------------------------------------------------------------ hooks
+    def _make_hook(self, name):
+        def hook(p):
+            if self._discovering:
+                self._order.append(name)
+                return
+            slot = self._slot.get(id(p))
+            if slot is None:
+                raise RuntimeError(f"GradReducer: parameter {name} produced a gradient but was unused on the discovery step "
+                                   "(call reset() when the set of participating parameters changes)")
+            b = self.buckets[slot[0]]
+            view = b.views[slot[1]]
+            if p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            b.pending -= 1
+            if b.pending == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: _Bucket):
+        if self.world == 1:
+            return
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg)
+                b.flat.mul_(1.0 / self.world)
+        else:
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    # ------------------------------------------------------------------ step protocol
+    def finish(self):
+        """Call after loss.backward(): joins the communication stream; on the discovery step performs the (non-overlapped)
+        reduction and builds the buckets for the following steps."""
+        if self._discovering:
+            self._build(self._order)
+            self._discovering = False
+            for b in self.buckets:
+                for p, v in zip(b.params, b.views):
+                    v.copy_(p.grad)
+                    p.grad = v
+                self._launch(b)
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        else:
+            for b in self.buckets:
+                if b.work is not None:
+                    b.work.wait()
+                    b.flat.mul_(1.0 / self.world)
+                    b.work = None
+        for b in self.buckets:
+            b.pending = len(b.params)
+
+    def zero_grad(self):
+        """Keeps param.grad pointing into the buckets (so the next hooks need no copy when autograd accumulates in place)
+        and zeroes them; equivalent to optimizer.zero_grad(set_to_none=False)."""
+        if self.buckets is None:
+            self.model.zero_grad(set_to_none=True)
+            return
+        for b in self.buckets:
+            for p in b.params:
+                p.grad = None
+
+    def reset(self):
+        self.buckets, self._slot, self._order, self._discovering = None, {}, [], True
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -215,6 +215,11 @@ class MaskedAutoencoderViT(nn.Module):
         self.decoder_norm = norm_layer(decoder_embed_dim)
         self.decoder_pred = nn.Linear(decoder_embed_dim, self.t_pred_patch_size * patch_size ** 2 * in_chans, bias=True)
         self.norm_pix_loss = norm_pix_loss
+        # bicubic (align_corners=False) high-res -> low-res grid resampling is a fixed linear map: build its matrix once
+        hr_h, hr_w = self.high_res_input_size[1], self.high_res_input_size[2]
+        eye = torch.eye(hr_h * hr_w).view(1, hr_h * hr_w, hr_h, hr_w)
+        lo = F.interpolate(eye, [self.input_size[1], self.input_size[2]], mode="bicubic", align_corners=False)
+        self.register_buffer("_interp_mat", lo.reshape(hr_h * hr_w, -1).t().contiguous(), persistent=False)
         self.initialize_weights()
         self.set_precision(precision)
 
@@ -307,14 +312,11 @@ class MaskedAutoencoderViT(nn.Module):
 
     # ------------------------------------------------------------------ pos tables
     def _spatial_table(self, table, high_res):
-        """models...:416-427 / :534-544: bicubic 32x32 -> 16x16 for low-res inputs, raw for 512-px (torch, autograd)."""
+        """models...:416-427 / :534-544: bicubic 32x32 -> 16x16 for low-res inputs (as its fixed linear map, ops.InterpTableFn), raw for 512-px."""
         C = table.shape[-1]
         if high_res:
             return table.reshape(-1, C)
-        hr_h, hr_w = self.high_res_input_size[1], self.high_res_input_size[2]
-        t = table.view(1, hr_h, hr_w, C).permute(0, 3, 1, 2)
-        t = F.interpolate(t, [self.input_size[1], self.input_size[2]], mode="bicubic", align_corners=False)
-        return t.permute(0, 2, 3, 1).reshape(self.input_size[1] * self.input_size[2], C).contiguous()
+        return ops.InterpTableFn.apply(table, self._interp_mat)
 
     def _is_high_res(self, H):
         return H == self.high_res_input_size[1] * self.high_res_patch_embed.patch_size[0]

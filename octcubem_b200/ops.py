@@ -506,3 +506,30 @@ class PatchEmbedFn(torch.autograd.Function):
         dw = gemm(GEMM_TN, dx2, patches, E, patches.shape[1], B * L, torch.float32).view(wshape)
         db = colsum(dx2)
         return None, dw, db, None, None, None
+
+
+class InterpTableFn(torch.autograd.Function):
+    """Bicubic 32x32 -> 16x16 resampling of a learnable spatial pos-embed table (models:419-421, :537-539) as the fixed
+    linear map it is:  table_lo [G_lo, C] = M [G_lo, G_hi] · table_hi [G_hi, C], with M = F.interpolate applied to the
+    identity once at construction.  fp32 CUDA-core GEMM (0.5 GFLOP); backward d_table_hi = M^T · d_table_lo."""
+
+    @staticmethod
+    def forward(ctx, table_hi, mat):
+        _chk(table_hi, mat)
+        G_lo, G_hi = mat.shape
+        C = table_hi.shape[-1]
+        t2 = table_hi.reshape(G_hi, C)
+        out = gemm(GEMM_NN, mat, t2, G_lo, C, G_hi, torch.float32, compute=OCT_F32)
+        ctx.save_for_backward(mat)
+        ctx.shape = table_hi.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mat,) = ctx.saved_tensors
+        G_lo, G_hi = mat.shape
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        C = dout.shape[-1]
+        d = gemm(GEMM_TN, mat, dout, G_hi, C, G_lo, torch.float32, compute=OCT_F32)
+        return d.view(ctx.shape), None

@@ -227,7 +227,7 @@ def test_mse_loss_frame_index_select():
 # ---------------------------------------------------------------- GEMMs / attention / patch-embed
 @pytest.mark.parametrize("layout", [GEMM_NT, GEMM_NN, GEMM_TN])
 @pytest.mark.parametrize("compute,M,N,K", [(OCT_F32, 130, 72, 40), (OCT_BF16, 384, 768, 512), (OCT_BF16, 3280, 1024, 1024),
-                                           (OCT_BF16, 200, 136, 72), (OCT_BF16, 4104, 512, 512)])
+                                           (OCT_BF16, 200, 136, 72), (OCT_BF16, 4104, 512, 512), (OCT_BF16, 512, 512, 8200), (OCT_BF16, 2048, 512, 32776)])
 def test_gemm(layout, compute, M, N, K):
     g = torch.Generator().manual_seed(M)
     dt = torch.float32 if compute == OCT_F32 else torch.bfloat16
@@ -235,7 +235,7 @@ def test_gemm(layout, compute, M, N, K):
     A = a.to(DEV) if layout != GEMM_TN else a.t().contiguous().to(DEV)
     Bm = b.to(DEV) if layout == GEMM_NT else b.t().contiguous().to(DEV)
     out = ops.gemm(layout, A, Bm, M, N, K, torch.float32, compute=compute)
-    assert rel(out, a.double() @ b.double().t()) < 2e-6
+    assert rel(out, a.double() @ b.double().t()) < (2e-6 if K <= 8192 else 2e-5)  # fp32 accumulation over K
 
 
 def test_linear_and_mlp_functions_bf16():
