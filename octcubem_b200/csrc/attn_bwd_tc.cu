@@ -9,11 +9,17 @@
 //     dQ_m = dS K               (SS, dS^T staged in smem and read as an MN-major A operand, K tile as MN-major B)
 // dV / dK accumulate in TMEM across the sweep; dQ_m tiles are reduced across CTAs with vector fp32 reductions into a
 // workspace that a small kernel scales and converts to bf16.
+//
+// 320 threads: warp 0 TMA, warp 1 MMA issuer, warps 2-9 softmax-backward.  Warps w and w+4 share a TMEM lane quarter and
+// split the 128 query columns of a tile in halves, so every scheduler has two warps feeding the SFU (the kernel is
+// ex2-bound for head_dim 32).  For head_dim 32 the bf16 P^T / dS^T live in their own TMEM columns, which lets the
+// issuer queue S^T/dP^T of the next query tile ahead of the dV/dK/dQ MMAs of the current one; for head_dim 64 TMEM is
+// too small for that (512 columns) and P^T / dS^T overwrite S^T / dP^T in place.
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int AB_T = 128, AB_THREADS = 192, AB_Q_STAGES = 2;
+constexpr int AB_T = 128, AB_THREADS = 320, AB_Q_STAGES = 2, AB_SM_THREADS = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int HD>
@@ -25,8 +31,20 @@ struct AbCfg {
   static constexpr int kDsBytes = 2 * 128 * 128;  // dS^T staging: two 64-column chunks of [128 kv rows x 128 B]
   // smem: K, V | Q[2], dO[2] | dS | lse2[2][128], delta[2][128] | barriers
   static constexpr int kSmem = 2 * kTileBytes + 2 * AB_Q_STAGES * kTileBytes + kDsBytes + 4 * 128 * 4 + 1024 + 256;
+  static constexpr bool kInPlace = (HD == 64);
   // TMEM columns
-  static constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + HD, kColDQ = 256 + 2 * HD;
+  static constexpr uint32_t kColST = 0, kColDPT = 128;
+  static constexpr uint32_t kColPT = kInPlace ? kColST : 256;    // bf16 P^T  (64 columns)
+  static constexpr uint32_t kColDST = kInPlace ? kColDPT : 320;  // bf16 dS^T (64 columns)
+  static constexpr uint32_t kColAcc = kInPlace ? 256 : 384;
+  static constexpr uint32_t kColDV = kColAcc, kColDK = kColAcc + HD, kColDQ = kColAcc + 2 * HD;
+  static_assert(kColDQ + HD <= 512, "TMEM budget");
+  // TMEM column offset (inside the P^T / dS^T region) of the 16-query slice k16 (= one UMMA K step, 8 columns).
+  // In place, each half-warpgroup keeps its bf16 output inside the fp32 columns it has itself consumed
+  // (half 0: columns [0,32), half 1: [64,96)), so the two halves never overwrite each other's unread scores.
+  __host__ __device__ static constexpr uint32_t slice_off(int k16) {
+    return kInPlace ? (uint32_t)((k16 >> 2) * 64 + (k16 & 3) * 8) : (uint32_t)(k16 * 8);
+  }
 };
 
 struct AbParams {
@@ -48,7 +66,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
                                                                     const AbParams p) {
   using C = AbCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = sK + C::kTileBytes;
   uint8_t* sQ = sV + C::kTileBytes;                       // [AB_Q_STAGES]
@@ -65,7 +84,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   uint64_t* dq_full = p_ready + 1;
   uint64_t* dq_free = dq_full + 1;
   uint64_t* acc_full = dq_free + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* p_free = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
@@ -77,10 +97,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     tc::mbar_init(kv_full, 1);
     for (int s = 0; s < AB_Q_STAGES; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
     tc::mbar_init(sdp_full, 1);
-    tc::mbar_init(p_ready, 128);
+    tc::mbar_init(p_ready, AB_SM_THREADS);
     tc::mbar_init(dq_full, 1);
-    tc::mbar_init(dq_free, 128);
+    tc::mbar_init(dq_free, AB_SM_THREADS);
     tc::mbar_init(acc_full, 1);
+    tc::mbar_init(p_free, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
@@ -111,11 +132,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       constexpr uint32_t idesc_acc = tc::make_idesc(tc::kFmtBF16, false, true, 128, HD);     // P^T dO, dS^T Q (TS)
       constexpr uint32_t idesc_dq = tc::make_idesc(tc::kFmtBF16, true, true, 128, HD);       // dS K (A MN-major)
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV), ds_addr = tc::smem_u32(sDS);
-      tc::mbar_wait(kv_full, 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int m = 0; m < n_q; ++m) {
-        tc::mbar_wait(&q_full[stage], phase);
-        tc::tcgen05_fence_after();
+      auto issue_sdp = [&](int stage) {  // S^T = K Q^T ; dP^T = V dO^T
         const uint32_t q_addr = tc::smem_u32(sQ + stage * C::kTileBytes);
         const uint32_t do_addr = tc::smem_u32(sDO + stage * C::kTileBytes);
 #pragma unroll
@@ -131,80 +148,134 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           tc::mma_ss(tmem_base + C::kColDPT, da, db, idesc_st, k != 0);
         }
         tc::mma_commit(sdp_full);
-        tc::mbar_wait(p_ready, m & 1);
+      };
+      tc::mbar_wait(kv_full, 0);
+      tc::mbar_wait(&q_full[0], 0);
+      tc::tcgen05_fence_after();
+      issue_sdp(0);
+      int stage = 0;
+      int nstage = 1 % AB_Q_STAGES; uint32_t nphase = (AB_Q_STAGES == 1) ? 1 : 0;
+      for (int m = 0; m < n_q; ++m) {
+        const bool more = (m + 1) < n_q;
+        const uint32_t q_addr = tc::smem_u32(sQ + stage * C::kTileBytes);
+        const uint32_t do_addr = tc::smem_u32(sDO + stage * C::kTileBytes);
+        auto issue_dv_dk = [&]() {
+#pragma unroll
+          for (int k = 0; k < 128 / 16; ++k) {  // dV += P^T dO
+            const uint64_t db = tc::make_smem_desc(do_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
+            tc::mma_ts(tmem_base + C::kColDV, tmem_base + C::kColPT + C::slice_off(k), db, idesc_acc, (m | k) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 128 / 16; ++k) {  // dK += dS^T Q
+            const uint64_t db = tc::make_smem_desc(q_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
+            tc::mma_ts(tmem_base + C::kColDK, tmem_base + C::kColDST + C::slice_off(k), db, idesc_acc, (m | k) != 0);
+          }
+        };
+        auto issue_dq = [&]() {
+          if (m > 0) {
+            tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM
+            tc::tcgen05_fence_after();
+          }
+#pragma unroll
+          for (int k = 0; k < 128 / 16; ++k) {  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
+            const uint64_t da = tc::make_smem_desc(ds_addr + k * 16 * 128, 128 * 128, 1024, tc::kSwz128);
+            const uint64_t db = tc::make_smem_desc(k_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
+            tc::mma_ss(tmem_base + C::kColDQ, da, db, idesc_dq, k != 0);
+          }
+          tc::mma_commit(dq_full);
+        };
+        auto issue_next_sdp = [&]() {
+          if (more) {
+            tc::mbar_wait(&q_full[nstage], nphase);
+            tc::tcgen05_fence_after();
+            issue_sdp(nstage);
+          }
+        };
+        tc::mbar_wait(p_ready, m & 1);  // softmax(m) done: fp32 S^T/dP^T consumed, bf16 P^T/dS^T (+ smem dS) ready
         tc::tcgen05_fence_after();
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {  // dV += P^T dO
-          const uint64_t db = tc::make_smem_desc(do_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
-          tc::mma_ts(tmem_base + C::kColDV, tmem_base + C::kColST + k * 8, db, idesc_acc, (m | k) != 0);
+        if (!C::kInPlace) {
+          // dQ first (its drain is on the threads' critical path), then the next tile's scores, then dV/dK, whose
+          // completion (p_free) is only needed when the threads want to overwrite the bf16 P^T/dS^T columns again
+          issue_dq();
+          issue_next_sdp();
+          issue_dv_dk();
+        } else {
+          issue_dv_dk();
+          issue_dq();
+          issue_next_sdp();  // overwrites P^T/dS^T in place: must follow their consumers in the in-order MMA pipe
         }
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {  // dK += dS^T Q
-          const uint64_t db = tc::make_smem_desc(q_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
-          tc::mma_ts(tmem_base + C::kColDK, tmem_base + C::kColDPT + k * 8, db, idesc_acc, (m | k) != 0);
-        }
-        if (m > 0) {
-          tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM
-          tc::tcgen05_fence_after();
-        }
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
-          const uint64_t da = tc::make_smem_desc(ds_addr + k * 16 * 128, 128 * 128, 1024, tc::kSwz128);
-          const uint64_t db = tc::make_smem_desc(k_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
-          tc::mma_ss(tmem_base + C::kColDQ, da, db, idesc_dq, k != 0);
-        }
+        tc::mma_commit(p_free);
         tc::mma_commit(&q_empty[stage]);
-        tc::mma_commit(dq_full);
-        if (++stage == AB_Q_STAGES) { stage = 0; phase ^= 1; }
+        if (more && ++nstage == AB_Q_STAGES) { nstage = 0; nphase ^= 1; }
+        if (++stage == AB_Q_STAGES) stage = 0;
       }
       tc::mma_commit(acc_full);
     }
     __syncwarp();
   } else {
-    // ===================== softmax-backward threads: thread <-> kv row =====================
+    // ===================== softmax-backward threads: thread <-> (kv row, half of the query columns) ==============
+    const int half = (warp - 2) >> 2;     // 0: query columns 0..63, 1: 64..127
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;  // kv row inside the tile
-    const int tid = row;
+    const int row = quarter * 32 + lane;  // kv row inside the tile == TMEM lane
+    const int tid = threadIdx.x - 64;     // 0..255
     const bool kv_ok = (n0 + row) < p.S;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const size_t bh = (size_t)b * p.H + h;
+    // per-query statistics of a q tile: threads 0..127 fetch lse (-> log2 domain), 128..255 fetch delta; the fetch for
+    // tile m+1 is issued one iteration ahead so its latency hides behind the softmax work of tile m
+    auto load_stat = [&](int m) -> float {
+      const int qi = m * AB_T + (tid & 127);
+      const bool ok = qi < p.S;
+      if (tid < 128) return ok ? p.lse[bh * p.S + qi] * kLog2e : INFINITY;
+      return ok ? p.delta[bh * p.S + qi] : 0.f;
+    };
+    float stat = load_stat(0);
     for (int m = 0; m < n_q; ++m) {
       const int slot = m & 1;
-      {  // per-query statistics of this q tile
-        const int qi = m * AB_T + tid;
-        const bool ok = qi < p.S;
-        sLse[slot * 128 + tid] = ok ? p.lse[bh * p.S + qi] * kLog2e : INFINITY;
-        sDelta[slot * 128 + tid] = ok ? p.delta[bh * p.S + qi] : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < 128) sLse[slot * 128 + tid] = stat;
+      else sDelta[slot * 128 + (tid & 127)] = stat;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (m + 1 < n_q) stat = load_stat(m + 1);
       tc::mbar_wait(sdp_full, m & 1);
       tc::tcgen05_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;  // 32-column chunk of the tile
         uint32_t s[32], dp[32];
         tc::tmem_ld_x32(lane_addr + C::kColST + c * 32, s);
         tc::tmem_ld_x32(lane_addr + C::kColDPT + c * 32, dp);
         tc::tmem_ld_wait();
         uint32_t pk[16], dk[16];
+        const float4* l4 = reinterpret_cast<const float4*>(sLse + slot * 128 + c * 32);
+        const float4* d4 = reinterpret_cast<const float4*>(sDelta + slot * 128 + c * 32);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int q0i = c * 32 + 2 * i;
-          const float l0 = sLse[slot * 128 + q0i], l1 = sLse[slot * 128 + q0i + 1];
-          float p0 = tc::fast_exp2(__uint_as_float(s[2 * i]) * p.scale_log2e - l0);
-          float p1 = tc::fast_exp2(__uint_as_float(s[2 * i + 1]) * p.scale_log2e - l1);
-          if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
-          const float d0 = p0 * (__uint_as_float(dp[2 * i]) - sDelta[slot * 128 + q0i]);
-          const float d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - sDelta[slot * 128 + q0i + 1]);
-          pk[i] = pack_bf16x2(p0, p1);
-          dk[i] = pack_bf16x2(d0, d1);
+        for (int i = 0; i < 8; ++i) {
+          const float4 lv = l4[i], dv = d4[i];
+          float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * i]), p.scale_log2e, -lv.x));
+          float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * i + 1]), p.scale_log2e, -lv.y));
+          float p2 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * i + 2]), p.scale_log2e, -lv.z));
+          float p3 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * i + 3]), p.scale_log2e, -lv.w));
+          if (!kv_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+          const float d0 = p0 * (__uint_as_float(dp[4 * i]) - dv.x);
+          const float d1 = p1 * (__uint_as_float(dp[4 * i + 1]) - dv.y);
+          const float d2 = p2 * (__uint_as_float(dp[4 * i + 2]) - dv.z);
+          const float d3 = p3 * (__uint_as_float(dp[4 * i + 3]) - dv.w);
+          pk[2 * i] = pack_bf16x2(p0, p1);
+          pk[2 * i + 1] = pack_bf16x2(p2, p3);
+          dk[2 * i] = pack_bf16x2(d0, d1);
+          dk[2 * i + 1] = pack_bf16x2(d2, d3);
         }
-        tc::tmem_st_x16(lane_addr + C::kColST + c * 16, pk);    // P^T  (bf16 pairs) over the consumed part of S^T
-        tc::tmem_st_x16(lane_addr + C::kColDPT + c * 16, dk);   // dS^T (bf16 pairs) over the consumed part of dP^T
-        // dS^T row -> smem (MN-major A operand of dQ = dS K): 64-column chunk (c>>1), 16-byte pieces (c&1)*4 .. +3
-        uint8_t* rowp = sDS + (c >> 1) * (128 * 128) + row * 128;
+        if (cc == 0 && m > 0) {  // dV/dK of the previous tile have finished reading the bf16 P^T / dS^T columns
+          tc::mbar_wait(p_free, (m - 1) & 1);
+          tc::tcgen05_fence_after();
+        }
+        tc::tmem_st_x16(lane_addr + C::kColPT + C::slice_off(2 * c), pk);    // P^T  (bf16 pairs), 2 K-slices
+        tc::tmem_st_x16(lane_addr + C::kColDST + C::slice_off(2 * c), dk);   // dS^T (bf16 pairs)
+        // dS^T row -> smem (MN-major A operand of dQ = dS K): 64-column chunk = half, 16-byte pieces cc*4 .. +3
+        uint8_t* rowp = sDS + half * (128 * 128) + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int piece = (c & 1) * 4 + i;
+          const int piece = cc * 4 + i;
           uint4 v = make_uint4(dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
           *reinterpret_cast<uint4*>(rowp + ((piece ^ (row & 7)) << 4)) = v;
         }
@@ -213,49 +284,44 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       tc::fence_proxy_async();  // st.shared (generic proxy) -> tcgen05.mma reads (async proxy)
       tc::tcgen05_fence_before();
       tc::mbar_arrive(p_ready);
-      // drain dQ_m and reduce it into the fp32 accumulator (row = query here!)
+      // drain dQ_m and reduce it into the fp32 accumulator (TMEM lane = query row here; the two halves split the columns)
       tc::mbar_wait(dq_full, m & 1);
       tc::tcgen05_fence_after();
-      float* dq_row = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T + row) * HD;
+      float* dq_row = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T + row) * HD + half * (HD / 2);
 #pragma unroll
       for (int c = 0; c < HD / 32; ++c) {
-        uint32_t o[32];
-        tc::tmem_ld_x32(lane_addr + C::kColDQ + c * 32, o);
+        uint32_t o[16];
+        tc::tmem_ld_x16(lane_addr + C::kColDQ + half * (HD / 2) + c * 16, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          red_add_v4(dq_row + c * 32 + i, __uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]),
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(dq_row + c * 16 + i, __uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]),
                      __uint_as_float(o[i + 3]));
       }
       tc::tcgen05_fence_before();
       tc::mbar_arrive(dq_free);
     }
-    // epilogue: dV, dK of this kv tile
+    // epilogue: half 0 stores dV, half 1 stores dK of this kv tile
     tc::mbar_wait(acc_full, 0);
     tc::tcgen05_fence_after();
     const int kv = n0 + row;
-    __nv_bfloat16* dk_row = p.dqkv + ((((size_t)b * p.S + kv) * 3 + 1) * p.H + h) * HD;
-    __nv_bfloat16* dv_row = dk_row + (size_t)p.H * HD;
+    const uint32_t col = half ? C::kColDK : C::kColDV;
+    const float sc = half ? p.scale : 1.f;
+    __nv_bfloat16* dst = p.dqkv + ((((size_t)b * p.S + kv) * 3 + (half ? 1 : 2)) * p.H + h) * HD;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t col = which ? C::kColDK : C::kColDV;
-      const float sc = which ? p.scale : 1.f;
-      __nv_bfloat16* dst = which ? dk_row : dv_row;
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld_x32(lane_addr + col + c * 32, o);
+      tc::tmem_ld_wait();
+      if (kv_ok) {
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t o[32];
-        tc::tmem_ld_x32(lane_addr + col + c * 32, o);
-        tc::tmem_ld_wait();
-        if (kv_ok) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[i]) * sc, __uint_as_float(o[i + 1]) * sc);
-            v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * sc, __uint_as_float(o[i + 3]) * sc);
-            v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * sc, __uint_as_float(o[i + 5]) * sc);
-            v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * sc, __uint_as_float(o[i + 7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c * 32 + i) = v;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * sc, __uint_as_float(o[i + 1]) * sc);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * sc, __uint_as_float(o[i + 3]) * sc);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * sc, __uint_as_float(o[i + 5]) * sc);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * sc, __uint_as_float(o[i + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i) = v;
         }
       }
     }

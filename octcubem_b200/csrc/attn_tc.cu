@@ -2,19 +2,22 @@
 // non-causal, dropout 0, softmax scale d^-0.5; the pip package's sm_100 build is an mma.sync (HMMA) kernel).
 // qkv packed [B,S,3,H,d] bf16 is read in place through one 4-D TMA map (d, 3H, S, B).
 //
-// Forward: one CTA = 128 query rows of one (batch, head).  192 threads:
-//   warp 0   TMA producer: Q once, then K_j / V_j tiles through a ring
-//   warp 1   MMA issuer:   S_j = Q K_j^T (SS, both K-major) into one of two TMEM S buffers; O += P_j V_j (TS: P read
-//            from TMEM as the A operand, V^T taken from the same row-major smem tile through an MN-major descriptor)
-//   warps 2-5 softmax: thread <-> query row (TMEM lane), online softmax in the log2 domain with lazy rescaling
-//            (O is only rescaled when the running max grows by more than 2^8), P written back over S as bf16.
-// S_{j+1} is computed while the softmax of tile j runs.  head_dim 64 uses 128B swizzle, head_dim 32 uses 64B swizzle
-// (the TMA row pitch equals the inner box extent).
+// Forward: one CTA = 256 query rows (two 128-row tiles) of one (batch, head).  320 threads:
+//   warp 0     TMA producer: both Q tiles once, then K_j / V_j tiles through a ring (shared by the two Q tiles)
+//   warp 1     MMA issuer:   S_t = Q_t K_j^T (SS, K-major x K-major) into the TMEM S buffer of tile t;
+//              O_t += P_t V_j (TS: P read from TMEM as the A operand, V taken from the same row-major smem tile through
+//              an MN-major descriptor).  Issue order QK0, QK1, PV0, QK0', PV1, QK1', ... so that one tile's softmax
+//              always overlaps the other tile's MMAs.
+//   warps 2-5  softmax warpgroup of Q tile 0, warps 6-9 of Q tile 1: thread <-> query row (TMEM lane), online softmax in
+//              the log2 domain with lazy rescaling (O is only rescaled when the running max grows by more than 2^8),
+//              P written back over S as bf16.
+// The kernel is MUFU(ex2)-bound for head_dim 32 (128 MMA flops per score element): two warps per scheduler
+// keep the SFU pipe busy.  head_dim 64 uses 128B swizzle, head_dim 32 uses 64B swizzle (TMA row pitch = inner box extent).
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int AT_BM = 128, AT_BN = 128, AT_THREADS = 192, AT_KV_STAGES = 4;
+constexpr int AT_BM = 128, AT_BN = 128, AT_QT = 2, AT_THREADS = 64 + AT_QT * 128, AT_KV_STAGES = 3;
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -24,8 +27,9 @@ struct AtCfg {
   static constexpr int kTileBytes = 128 * kRowBytes;             // one 128-row Q / K / V tile
   static constexpr uint32_t kSwz = (HD == 64) ? tc::kSwz128 : tc::kSwz64;
   static constexpr uint32_t kSBO = 8 * kRowBytes;                // 8-row swizzle atom
-  static constexpr int kSmem = kTileBytes * (1 + 2 * AT_KV_STAGES) + 1024 + 256;
-  static constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO = 256;
+  static constexpr int kSmem = kTileBytes * (AT_QT + 2 * AT_KV_STAGES) + 1024 + 256;
+  static constexpr uint32_t kColS = 0;      // S_t at kColS + 128 t
+  static constexpr uint32_t kColO = 256;    // O_t at kColO + HD t
 };
 
 struct AtParams {
@@ -40,29 +44,33 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
                                                                     const AtParams p) {
   using C = AtCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + C::kTileBytes;
-  uint8_t* sV = sK + AT_KV_STAGES * C::kTileBytes;
+  // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                   // [AT_QT]
+  uint8_t* sK = smem + AT_QT * C::kTileBytes;           // [AT_KV_STAGES]
+  uint8_t* sV = sK + AT_KV_STAGES * C::kTileBytes;      // [AT_KV_STAGES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_KV_STAGES * C::kTileBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + AT_KV_STAGES;
-  uint64_t* s_full = kv_empty + AT_KV_STAGES;  // [2]
-  uint64_t* p_full = s_full + 2;               // [2]
-  uint64_t* o_done = p_full + 2;               // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* s_full = kv_empty + AT_KV_STAGES;  // [AT_QT]
+  uint64_t* p_full = s_full + AT_QT;           // [AT_QT]
+  uint64_t* o_done = p_full + AT_QT;           // [AT_QT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + AT_QT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (AT_QT * AT_BM), h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.S + AT_BN - 1) / AT_BN;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
     tc::mbar_init(q_full, 1);
     for (int s = 0; s < AT_KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_full[s], 128); }
-    tc::mbar_init(o_done, 1);
+    for (int t = 0; t < AT_QT; ++t) {
+      tc::mbar_init(&s_full[t], 1);
+      tc::mbar_init(&p_full[t], 128);
+      tc::mbar_init(&o_done[t], 1);
+    }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
@@ -74,8 +82,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(q_full, C::kTileBytes);
-      tc::tma_load_4d(sQ, &tmap_qkv, q_full, 0, h, q0, b);
+      tc::mbar_arrive_expect_tx(q_full, AT_QT * C::kTileBytes);
+#pragma unroll
+      for (int t = 0; t < AT_QT; ++t) tc::tma_load_4d(sQ + t * C::kTileBytes, &tmap_qkv, q_full, 0, h, q0 + t * AT_BM, b);
       int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         tc::mbar_wait(&kv_empty[stage], phase ^ 1);
@@ -90,122 +99,154 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     if (lane == 0) {
       constexpr uint32_t idesc_qk = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, AT_BN);
       constexpr uint32_t idesc_pv = tc::make_idesc(tc::kFmtBF16, false, true, AT_BM, HD);
-      const uint32_t q_addr = tc::smem_u32(sQ);
-      auto issue_qk = [&](int j, int stage) {
+      auto issue_qk = [&](int t, int stage) {
+        const uint32_t q_addr = tc::smem_u32(sQ + t * C::kTileBytes);
         const uint32_t k_addr = tc::smem_u32(sK + stage * C::kTileBytes);
-        const uint32_t tmem_s = tmem_base + ((j & 1) ? C::kColS1 : C::kColS0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint64_t da = tc::make_smem_desc(q_addr + k * 32, 16, C::kSBO, C::kSwz);
           const uint64_t db = tc::make_smem_desc(k_addr + k * 32, 16, C::kSBO, C::kSwz);
-          tc::mma_ss(tmem_s, da, db, idesc_qk, k != 0);
+          tc::mma_ss(tmem_base + C::kColS + t * 128, da, db, idesc_qk, k != 0);
         }
-        tc::mma_commit(&s_full[j & 1]);
+        tc::mma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j, int stage) {
+        const uint32_t v_addr = tc::smem_u32(sV + stage * C::kTileBytes);
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k) {
+          // V as an MN-major B operand: 16 kv rows per step; one MN chunk (= HD elements) so LBO is unused
+          const uint64_t db = tc::make_smem_desc(v_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
+          tc::mma_ts(tmem_base + C::kColO + t * HD, tmem_base + C::kColS + t * 128 + k * 8, db, idesc_pv, (j | k) != 0);
+        }
+        tc::mma_commit(&o_done[t]);
       };
       tc::mbar_wait(q_full, 0);
-      int stage = 0; uint32_t phase = 0;          // ring position of tile j
-      int nstage = 0; uint32_t nphase = 0;        // ring position of the next tile whose K has not been consumed yet
       tc::mbar_wait(&kv_full[0], 0);
       tc::tcgen05_fence_after();
       issue_qk(0, 0);
-      if (++nstage == AT_KV_STAGES) { nstage = 0; nphase ^= 1; }
+      issue_qk(1, 0);
+      int stage = 0;                          // ring position of tile j
+      int nstage = 1 % AT_KV_STAGES; uint32_t nphase = (AT_KV_STAGES == 1) ? 1 : 0;  // ring position of tile j+1
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {  // S_{j+1} = Q K_{j+1}^T overlaps softmax(j)
+        const bool more = (j + 1) < n_kv;
+        tc::mbar_wait(&p_full[0], j & 1);    // P_0(j) in TMEM (and O_0 rescaled if needed)
+        tc::tcgen05_fence_after();
+        issue_pv(0, j, stage);
+        if (more) {
           tc::mbar_wait(&kv_full[nstage], nphase);
           tc::tcgen05_fence_after();
-          issue_qk(j + 1, nstage);
+          issue_qk(0, nstage);                // overlaps softmax of tile 1
+        }
+        tc::mbar_wait(&p_full[1], j & 1);
+        tc::tcgen05_fence_after();
+        issue_pv(1, j, stage);
+        tc::mma_commit(&kv_empty[stage]);     // K_j, V_j fully consumed
+        if (more) {
+          issue_qk(1, nstage);                // overlaps softmax of tile 0
           if (++nstage == AT_KV_STAGES) { nstage = 0; nphase ^= 1; }
         }
-        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM, O rescaled if needed
-        tc::tcgen05_fence_after();
-        const uint32_t v_addr = tc::smem_u32(sV + stage * C::kTileBytes);
-        const uint32_t tmem_p = tmem_base + ((j & 1) ? C::kColS1 : C::kColS0);
-#pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k) {
-          // V^T as an MN-major B operand: 16 kv rows per step; one MN chunk (= HD elements) so LBO is unused
-          const uint64_t db = tc::make_smem_desc(v_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
-          tc::mma_ts(tmem_base + C::kColO, tmem_p + k * 8, db, idesc_pv, (j | k) != 0);
-        }
-        tc::mma_commit(&kv_empty[stage]);
-        tc::mma_commit(o_done);
-        if (++stage == AT_KV_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == AT_KV_STAGES) stage = 0;
       }
-      (void)phase;
     }
     __syncwarp();
   } else {
-    // ===================== softmax / correction / epilogue =====================
+    // ===================== softmax / correction / epilogue: warpgroup t owns Q tile t =====================
+    const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t tmem_s = lane_addr + C::kColS + t * 128;
+    const uint32_t tmem_o = lane_addr + C::kColO + t * HD;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      const uint32_t tmem_s = lane_addr + ((j & 1) ? C::kColS1 : C::kColS0);
-      tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc::mbar_wait(&s_full[t], j & 1);
       tc::tcgen05_fence_after();
-      uint32_t sr[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tc::tmem_ld_x32(tmem_s + c * 32, sr[c]);
-      tc::tmem_ld_wait();
       const int valid = p.S - j * AT_BN;  // columns >= valid are out of range (TMA zero-filled K rows)
-      float mx = -INFINITY;
+      // pass 1: row maximum of the raw scores (TMEM reads are cheap; keeping 128 scores live would cost 128 registers).
+      // Chunk c+1 is requested before chunk c is consumed (register double buffer) so the TMEM latency stays hidden.
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      uint32_t sr[2][32];
+      tc::tmem_ld_x32(tmem_s, sr[0]);
+      tc::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 4; ++c) {
+        if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
+        uint32_t(&cur)[32] = sr[c & 1];
+        if (valid < AT_BN) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(sr[c][i]);
-          if (valid < AT_BN && c * 32 + i >= valid) { s = -INFINITY; sr[c][i] = __float_as_uint(s); }
-          mx = fmaxf(mx, s);
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) cur[i] = 0xff800000u;  // -inf
         }
-      const float m_tile = mx * p.scale_log2e;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(cur[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(cur[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(cur[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(cur[i + 3]));
+        }
+        if (c < 3) tc::tmem_ld_wait();
+      }
+      tc::tmem_ld_x32(tmem_s, sr[0]);  // first chunk of pass 2, in flight during the rescale decision
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2e;
       const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? m_tile : m;
         if (j > 0) {
           const float factor = need ? tc::fast_exp2(m - m_new) : 1.f;
-          tc::mbar_wait(o_done, (j - 1) & 1);  // O += P_{j-1} V_{j-1} has landed
+          tc::mbar_wait(&o_done[t], (j - 1) & 1);  // O_t += P_t(j-1) V_{j-1} has landed
           tc::tcgen05_fence_after();
 #pragma unroll
           for (int c = 0; c < HD / 32; ++c) {
             uint32_t o[32];
-            tc::tmem_ld_x32(lane_addr + C::kColO + c * 32, o);
+            tc::tmem_ld_x32(tmem_o + c * 32, o);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tc::tmem_st_x32(lane_addr + C::kColO + c * 32, o);
+            tc::tmem_st_x32(tmem_o + c * 32, o);
           }
           l *= factor;
         }
         m = m_new;
       }
-      float lsum = 0.f;
+      // pass 2: P = exp2(s * c - m) as bf16 pairs written over the consumed part of S (chunk c occupies columns
+      // [16c, 16c+16) while the unread chunks start at 32(c+1), so the in-place overwrite never races ahead)
+      float l0 = 0.f, l1 = 0.f;
+      tc::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
+        uint32_t(&cur)[32] = sr[c & 1];
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = tc::fast_exp2(__uint_as_float(sr[c][2 * i]) * p.scale_log2e - m);
-          const float p1 = tc::fast_exp2(__uint_as_float(sr[c][2 * i + 1]) * p.scale_log2e - m);
-          lsum += p0 + p1;
+          float p0 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2e, -m));
+          float p1 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2e, -m));
+          if (valid < AT_BN) {
+            if (c * 32 + 2 * i >= valid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+          }
+          l0 += p0;
+          l1 += p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
-        tc::tmem_st_x16(tmem_s + c * 16, pk);  // P (bf16 pairs) overwrites the first 64 columns of this S buffer
+        if (c < 3) tc::tmem_ld_wait();         // chunk c+1 is in registers before chunk c's columns are overwritten
+        tc::tmem_st_x16(tmem_s + c * 16, pk);  // in place: bf16 chunk c -> columns [16c,16c+16), all read already
       }
-      l += lsum;
+      l += l0 + l1;
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&p_full[j & 1]);
+      tc::mbar_arrive(&p_full[t]);
     }
     // epilogue: O / l -> bf16, lse
-    tc::mbar_wait(o_done, (n_kv - 1) & 1);
+    tc::mbar_wait(&o_done[t], (n_kv - 1) & 1);
     tc::tcgen05_fence_after();
-    const int qi = q0 + row;
+    const int qi = q0 + t * AT_BM + row;
     const float inv = 1.f / l;
     __nv_bfloat16* orow = p.out + (((size_t)b * p.S + qi) * p.H + h) * HD;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
       uint32_t o[32];
-      tc::tmem_ld_x32(lane_addr + C::kColO + c * 32, o);
+      tc::tmem_ld_x32(tmem_o + c * 32, o);
       tc::tmem_ld_wait();
       if (qi < p.S) {
 #pragma unroll
@@ -253,7 +294,7 @@ int launch_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int
   }
   AtParams p;
   p.S = (int)S; p.H = (int)H; p.scale_log2e = scale * kLog2e; p.out = (__nv_bfloat16*)out; p.lse = lse;
-  dim3 grid((unsigned)ceil_div64(S, AT_BM), (unsigned)H, (unsigned)B);
+  dim3 grid((unsigned)ceil_div64(S, AT_QT * AT_BM), (unsigned)H, (unsigned)B);
   attn_fwd_tc_kernel<HD><<<grid, AT_THREADS, C::kSmem, st>>>(map, p);
   return oct_check_launch("oct_attn_fwd(bf16)");
 }
@@ -269,5 +310,3 @@ int oct_attn_fwd_tc(const void* qkv, void* out, float* lse, int64_t B, int64_t S
   oct_set_error("oct_attn_fwd(bf16): head dim %lld unsupported by the tcgen05 kernel (32 or 64)", (long long)d);
   return OCT_ERR_UNSUPPORTED;
 }
-
-// ---- backward: see attn_bwd_tc.cu ----

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(PE_THREADS, 2) patch_embed_tc_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tmap_w,
                                                                        const PeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + PE_STAGES * PE_A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PE_STAGES * PE_STAGE_BYTES);
