@@ -147,6 +147,12 @@ def workload_name():
 # ----------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------------
+def _watchdog(seconds):
+    time.sleep(seconds)
+    print(f"[bench] watchdog: still running after {seconds} s, aborting", file=sys.stderr, flush=True)
+    os._exit(3)
+
+
 def main_b200(args):
     import torch.distributed as dist
     from octcubem_b200 import _lib, models_mae, ops
@@ -155,6 +161,9 @@ def main_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+    threading.Thread(target=_watchdog, args=(1500,), daemon=True).start()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -304,9 +313,12 @@ def main_b200(args):
             line["cpu_baseline"] = {"value": r["value"], "unit": "volumes/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # leave without NCCL teardown: destroying a communicator whose kernels live in a captured graph can block; every
+    # rank has passed the final barrier inside timed(), nothing else is in flight
+    sys.stdout.flush()
+    sys.stderr.flush()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 def dominant_kernel_roofline(ops, dev, pk):

@@ -223,17 +223,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const size_t bh = (size_t)b * p.H + h;
     // per-query statistics of a q tile: threads 0..127 fetch lse (-> log2 domain), 128..255 fetch delta; the fetch for
     // tile m+1 is issued one iteration ahead so its latency hides behind the softmax work of tile m
-    auto load_stat = [&](int m) -> float {
-      const int qi = m * AB_T + (tid & 127);
-      const bool ok = qi < p.S;
-      if (tid < 128) return ok ? p.lse[bh * p.S + qi] * kLog2e : INFINITY;
-      return ok ? p.delta[bh * p.S + qi] : 0.f;
+    auto load_stat = [&](int m) -> float {  // raw value; transformed only when it is stored (keeps the LDG in flight)
+      const int qi = min(m * AB_T + (tid & 127), p.S - 1);
+      return (tid < 128) ? p.lse[bh * p.S + qi] : p.delta[bh * p.S + qi];
     };
     float stat = load_stat(0);
     for (int m = 0; m < n_q; ++m) {
       const int slot = m & 1;
-      if (tid < 128) sLse[slot * 128 + tid] = stat;
-      else sDelta[slot * 128 + (tid & 127)] = stat;
+      {
+        const bool ok = (m * AB_T + (tid & 127)) < p.S;
+        if (tid < 128) sLse[slot * 128 + tid] = ok ? stat * kLog2e : INFINITY;
+        else sDelta[slot * 128 + (tid & 127)] = ok ? stat : 0.f;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (m + 1 < n_q) stat = load_stat(m + 1);
       tc::mbar_wait(sdp_full, m & 1);

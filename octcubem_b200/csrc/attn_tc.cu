@@ -39,6 +39,92 @@ struct AtParams {
   float* lse;          // [B,H,S]
 };
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // 3-input max (sm_100)
+  return d;
+}
+
+// One 128x128 score tile of one query row: online-softmax update (m, l in the log2 domain), P written over S as bf16.
+// kMasked = last kv tile (columns >= valid do not exist); the common full tile carries no per-element predicates.
+template <int HD, bool kMasked>
+__device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, uint64_t* o_done, int j, int valid,
+                                             float scale_log2e, float& m, float& l) {
+  // pass 1: row maximum of the raw scores (TMEM reads are cheap; keeping 128 scores live would cost 128 registers).
+  // Chunk c+1 is requested before chunk c is consumed (register double buffer) so the TMEM latency stays hidden.
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  uint32_t sr[2][32];
+  tc::tmem_ld_x32(tmem_s, sr[0]);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
+    uint32_t(&cur)[32] = sr[c & 1];
+    if (kMasked) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i >= valid) cur[i] = 0xff800000u;  // -inf
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      mx0 = max3(mx0, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+      mx1 = max3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+    }
+    if (c < 3) tc::tmem_ld_wait();
+  }
+  tc::tmem_ld_x32(tmem_s, sr[0]);  // first chunk of pass 2, in flight during the rescale decision
+  const float m_tile = fmaxf(mx0, mx1) * scale_log2e;
+  const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
+  if (__any_sync(0xffffffffu, need)) {
+    const float m_new = need ? m_tile : m;
+    if (j > 0) {
+      const float factor = need ? tc::fast_exp2(m - m_new) : 1.f;
+      tc::mbar_wait(o_done, (j - 1) & 1);  // O += P(j-1) V_{j-1} has landed
+      tc::tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld_x32(tmem_o + c * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+        tc::tmem_st_x32(tmem_o + c * 32, o);
+      }
+      l *= factor;
+    }
+    m = m_new;
+  }
+  // pass 2: P = exp2(s * c - m) as bf16 pairs written over the consumed part of S (chunk c occupies columns
+  // [16c, 16c+16) while the unread chunks start at 32(c+1), so the in-place overwrite never races ahead)
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
+    uint32_t(&cur)[32] = sr[c & 1];
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float p0 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i]), scale_log2e, -m));
+      float p1 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), scale_log2e, -m));
+      float p2 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 2]), scale_log2e, -m));
+      float p3 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 3]), scale_log2e, -m));
+      if (kMasked) {
+        if (c * 32 + 2 * i >= valid) p0 = 0.f;
+        if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+        if (c * 32 + 2 * i + 2 >= valid) p2 = 0.f;
+        if (c * 32 + 2 * i + 3 >= valid) p3 = 0.f;
+      }
+      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+      pk[i] = pack_bf16x2(p0, p1);
+      pk[i + 1] = pack_bf16x2(p2, p3);
+    }
+    if (c < 3) tc::tmem_ld_wait();         // chunk c+1 is in registers before chunk c's columns are overwritten
+    tc::tmem_st_x16(tmem_s + c * 16, pk);  // in place: bf16 chunk c -> columns [16c,16c+16), all read already
+  }
+  l += (l0 + l1) + (l2 + l3);
+}
+
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                     const AtParams p) {
@@ -162,77 +248,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       tc::mbar_wait(&s_full[t], j & 1);
       tc::tcgen05_fence_after();
       const int valid = p.S - j * AT_BN;  // columns >= valid are out of range (TMA zero-filled K rows)
-      // pass 1: row maximum of the raw scores (TMEM reads are cheap; keeping 128 scores live would cost 128 registers).
-      // Chunk c+1 is requested before chunk c is consumed (register double buffer) so the TMEM latency stays hidden.
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      uint32_t sr[2][32];
-      tc::tmem_ld_x32(tmem_s, sr[0]);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
-        uint32_t(&cur)[32] = sr[c & 1];
-        if (valid < AT_BN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) cur[i] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(cur[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(cur[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(cur[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(cur[i + 3]));
-        }
-        if (c < 3) tc::tmem_ld_wait();
-      }
-      tc::tmem_ld_x32(tmem_s, sr[0]);  // first chunk of pass 2, in flight during the rescale decision
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2e;
-      const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = need ? m_tile : m;
-        if (j > 0) {
-          const float factor = need ? tc::fast_exp2(m - m_new) : 1.f;
-          tc::mbar_wait(&o_done[t], (j - 1) & 1);  // O_t += P_t(j-1) V_{j-1} has landed
-          tc::tcgen05_fence_after();
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            tc::tmem_ld_x32(tmem_o + c * 32, o);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tc::tmem_st_x32(tmem_o + c * 32, o);
-          }
-          l *= factor;
-        }
-        m = m_new;
-      }
-      // pass 2: P = exp2(s * c - m) as bf16 pairs written over the consumed part of S (chunk c occupies columns
-      // [16c, 16c+16) while the unread chunks start at 32(c+1), so the in-place overwrite never races ahead)
-      float l0 = 0.f, l1 = 0.f;
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
-        uint32_t(&cur)[32] = sr[c & 1];
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2e, -m));
-          float p1 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2e, -m));
-          if (valid < AT_BN) {
-            if (c * 32 + 2 * i >= valid) p0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-          }
-          l0 += p0;
-          l1 += p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        if (c < 3) tc::tmem_ld_wait();         // chunk c+1 is in registers before chunk c's columns are overwritten
-        tc::tmem_st_x16(tmem_s + c * 16, pk);  // in place: bf16 chunk c -> columns [16c,16c+16), all read already
-      }
-      l += l0 + l1;
+      if (valid >= AT_BN)
+        softmax_tile<HD, false>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
+      else
+        softmax_tile<HD, true>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&p_full[t]);
