@@ -7,20 +7,28 @@
 //     dP^T = V dO_h^T           (SS)                             dS^T = P^T o (dP^T - delta)
 //     dV  += P^T  dO_h          (TS, dO rows as MN-major B)      dK  += dS^T Q_h   (TS, Q rows as MN-major B)
 //     dQ_m = dS K               (SS, once per 128-row query tile: dS^T staged in smem, read as an MN-major A operand)
-// dV / dK accumulate in TMEM across the sweep; dQ_m tiles are reduced across CTAs with vector fp32 reductions into a
-// workspace that a small kernel scales and converts to bf16.
+// dV / dK accumulate in TMEM across the sweep; dQ_m tiles go TMEM -> registers -> swizzled smem -> one asynchronous
+// cp.reduce.async.bulk (.add.f32) into an fp32 workspace that a small kernel scales and converts to bf16.
 //
-// 192 threads: warps 0-3 softmax-backward (thread <-> kv row), warp 4 TMA, warp 5 MMA issuer.  The 64-column sub-tiles
-// keep the TMEM footprint at 128 + 3*head_dim columns, so for head_dim 32 TWO CTAs share an SM (224 of 256 columns each,
-// 83 KB smem each): while one CTA's threads wait for their MMAs, the other CTA's threads keep the SFU busy (the kernel
-// is ex2-bound for head_dim 32).  bf16 P^T / dS^T overwrite the fp32 S^T / dP^T columns in place.
+// Measured facts that shape the schedule (profiles/r1_attention_ncu.md): a tcgen05.mma with N <= 128 occupies the
+// tensor pipe for ~64 cycles whatever N is (the 128x16 A operand has to be streamed), so the 28 small MMAs of one
+// (kv tile, q tile) pair cost ~1800 cycles — the kernel is bound by the in-order MMA stream, not by FLOPs or ex2.
+// Therefore the MMA stream must never wait for the softmax threads:
+//   * the fp32 S^T / dP^T sub-tiles are double-buffered in TMEM (2 x 128 columns); the scores of sub-tile i+2 are queued
+//     behind the gradient MMAs of sub-tile i, while the threads are still working on sub-tile i+1;
+//   * bf16 P^T / dS^T overwrite the fp32 columns their own thread has consumed (no extra columns, no cross-warp hazard);
+//   * the dS^T smem tile is double-buffered and the dQ drain of tile m is deferred by one sub-tile, so the threads
+//     never stall on the tail of the queue.
+// 320 threads: warps 0-7 softmax-backward (two warps per TMEM lane quarter, 32 query columns each -> two warps per
+// scheduler hide each other's TMEM / SFU latency), warp 8 TMA producer, warp 9 MMA issuer (highest warp id: the
+// scheduler arbitrates highest-id first and everything waits on this serial chain).
 #include "tc_common.cuh"
 #include <type_traits>
 #include <cstdlib>
 
 namespace {
 
-constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 192, AB_Q_STAGES = 2;
+constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 320, AB_SM_THREADS = 256, AB_Q_STAGES = 2;
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int HD>
@@ -29,16 +37,17 @@ struct AbCfg {
   static constexpr int kTileBytes = 128 * kRowBytes;
   static constexpr uint32_t kSwz = (HD == 64) ? tc::kSwz128 : tc::kSwz64;
   static constexpr uint32_t kSBO = 8 * kRowBytes;
-  static constexpr int kDsBytes = 2 * 128 * 128;  // dS^T staging: two 64-column chunks of [128 kv rows x 128 B]
-  // smem: K, V | Q[2], dO[2] | dS | lse2[2][128], delta[2][128] | barriers
+  static constexpr int kDsBytes = 2 * 128 * 128;  // one dS^T staging tile: two 64-query chunks of [128 kv rows x 128 B]
   static constexpr int kDqBytes = 128 * HD * 4;   // fp32 dQ tile staged for the bulk reduce (16-byte chunks XOR-swizzled)
-  static constexpr int kSmem = 2 * kTileBytes + 2 * AB_Q_STAGES * kTileBytes + kDsBytes + kDqBytes + 4 * 128 * 4 + 1024 + 256;
-  static constexpr int kCtasPerSm = (HD == 32) ? 2 : 1;
-  static constexpr uint32_t kTmemCols = (HD == 32) ? 256 : 512;
-  // TMEM columns: fp32 S^T / dP^T sub-tiles (64 columns each; bf16 P^T / dS^T reuse their first 32 columns)
-  static constexpr uint32_t kColST = 0, kColDPT = 64;
-  static constexpr uint32_t kColDV = 128, kColDK = 128 + HD, kColDQ = 128 + 2 * HD;
-  static_assert(kColDQ + HD <= kTmemCols, "TMEM budget");
+  // smem: K, V | Q[2], dO[2] | dS[2] | dQ staging | lse2[2][128], delta[2][128] | barriers
+  static constexpr int kSmem = 2 * kTileBytes + 2 * AB_Q_STAGES * kTileBytes + 2 * kDsBytes + kDqBytes + 4 * 128 * 4 + 1024 + 256;
+  // TMEM columns: stage s of the fp32 sub-tiles: S^T at 128 s, dP^T at 128 s + 64; accumulators behind them
+  static constexpr uint32_t kColST = 0, kColDPT = 64, kStageCols = 128;
+  static constexpr uint32_t kColDV = 256, kColDK = 256 + HD, kColDQ = 256 + 2 * HD;
+  static_assert(kColDQ + HD <= 512, "TMEM budget");
+  // bf16 K-slice k (16 queries, 8 columns) of a sub-tile: the warp that owns query columns [32 c, 32 c + 32) writes its
+  // bf16 output over its own fp32 columns -> slices 0,1 at columns 0,8 and slices 2,3 at columns 32,40
+  __host__ __device__ static constexpr uint32_t slice_off(int k) { return (uint32_t)((k >> 1) * 32 + (k & 1) * 8); }
 };
 
 struct AbParams {
@@ -46,26 +55,21 @@ struct AbParams {
   float scale, scale_log2e;
   const float* lse;     // [B,H,S]
   const float* delta;   // [B,H,S]
-  float* dq_acc;        // [B,H,Spad,HD] fp32, zero-initialised
+  float* dq_acc;        // [B,H,Spad,HD] fp32, zero-initialised, 16-byte chunks of each row XOR-swizzled
   __nv_bfloat16* dqkv;  // [B,S,3,H,HD]
-  int dbg;              // OCT_ATTN_BWD_DBG experiment switches (0 in production): 1 no dQ reds, 2 no dS smem store,
-                        // 4 no dP^T load, 8 no ex2
+  int dbg;              // OCT_ATTN_BWD_DBG=16: record a cycle trace of CTA (1,0,0) (diagnostics only)
 };
 
-__device__ long long g_ab_trace[4 * 16];
-#define AB_TRACE(id)                                                                                       \
-  do {                                                                                                    \
-    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 5 || warp == 0) && \
-        i >= 4 && i < 8)                                                                                  \
-      g_ab_trace[(i - 4) * 16 + (id)] = clock64();                                                        \
+__device__ long long g_ab_trace[8 * 16];
+#define AB_TRACE(id)                                                                                              \
+  do {                                                                                                           \
+    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 9 || warp == 0) && \
+        i >= 8 && i < 16)                                                                                        \
+      g_ab_trace[(i - 8) * 16 + (id)] = clock64();                                                               \
   } while (0)
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <int HD>
-__global__ void __launch_bounds__(AB_THREADS, AbCfg<HD>::kCtasPerSm)
+__global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const AbParams p) {
   using C = AbCfg<HD>;
@@ -76,18 +80,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint8_t* sV = sK + C::kTileBytes;
   uint8_t* sQ = sV + C::kTileBytes;                       // [AB_Q_STAGES]
   uint8_t* sDO = sQ + AB_Q_STAGES * C::kTileBytes;        // [AB_Q_STAGES]
-  uint8_t* sDS = sDO + AB_Q_STAGES * C::kTileBytes;       // 32 KB, 1024-aligned (all tiles are multiples of 8 KB)
-  uint8_t* sDQ = sDS + C::kDsBytes;                        // [128][HD] fp32, swizzled
+  uint8_t* sDS = sDO + AB_Q_STAGES * C::kTileBytes;       // [2] x 32 KB, 1024-aligned (all tiles are multiples of 8 KB)
+  uint8_t* sDQ = sDS + 2 * C::kDsBytes;                   // [128][HD] fp32, swizzled
   float* sLse = reinterpret_cast<float*>(sDQ + C::kDqBytes);  // [2][128]
   float* sDelta = sLse + 2 * 128;                             // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * 128);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;                 // [2]
   uint64_t* q_empty = q_full + AB_Q_STAGES;    // [2]
-  uint64_t* sdp_full = q_empty + AB_Q_STAGES;  // once per sub-tile
-  uint64_t* p_ready = sdp_full + 1;            // once per sub-tile (128 arrivals)
-  uint64_t* dq_full = p_ready + 1;             // once per query tile
-  uint64_t* dq_free = dq_full + 1;             // once per query tile (128 arrivals)
+  uint64_t* sdp_full = q_empty + AB_Q_STAGES;  // [2] per fp32 stage, one completion every other sub-tile
+  uint64_t* p_ready = sdp_full + 2;            // [2] per fp32 stage (256 arrivals)
+  uint64_t* dq_full = p_ready + 2;             // once per query tile
+  uint64_t* dq_free = dq_full + 1;             // once per query tile (256 arrivals)
   uint64_t* acc_full = dq_free + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
@@ -96,28 +100,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   const int n_q = (p.S + AB_T - 1) / AB_T;
   const int n_sub = 2 * n_q;
 
-  // Warp roles: 0-3 softmax-backward, 4 TMA producer, 5 MMA issuer.  The scheduler arbitrates highest-warp-id first
-  // (B300_MICROARCH.md), so the single-threaded issuer — whose serial chain everything else waits on — must outrank the
-  // ALU-heavy softmax warp it shares a scheduler with.
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
     tc::prefetch_tmap(&tmap_do);
     tc::mbar_init(kv_full, 1);
     for (int s = 0; s < AB_Q_STAGES; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
-    tc::mbar_init(sdp_full, 1);
-    tc::mbar_init(p_ready, 128);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&sdp_full[s], 1); tc::mbar_init(&p_ready[s], AB_SM_THREADS); }
     tc::mbar_init(dq_full, 1);
-    tc::mbar_init(dq_free, 128);
+    tc::mbar_init(dq_free, AB_SM_THREADS);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 5) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 9) tc::tmem_alloc<512>(tmem_slot);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(kv_full, 2 * C::kTileBytes);
@@ -132,7 +132,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         if (++stage == AB_Q_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_st = tc::make_idesc(tc::kFmtBF16, false, false, 128, AB_SUB);  // K Q_h^T, V dO_h^T
@@ -140,8 +140,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       constexpr uint32_t idesc_dq = tc::make_idesc(tc::kFmtBF16, true, true, 128, HD);         // dS K (A MN-major)
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV), ds_addr = tc::smem_u32(sDS);
       // Descriptors are built once; inside the loop only their 14-bit start-address field (units of 16 B) is advanced.
-      // The issuing thread shares its scheduler with busy softmax warps, so every instruction saved here shortens
-      // the serial MMA-issue chain the softmax threads wait on.
       const uint64_t dK_kmaj = tc::make_smem_desc(k_addr, 16, C::kSBO, C::kSwz);                 // K as K-major A
       const uint64_t dV_kmaj = tc::make_smem_desc(v_addr, 16, C::kSBO, C::kSwz);                 // V as K-major A
       const uint64_t dK_mn = tc::make_smem_desc(k_addr, C::kTileBytes, C::kSBO, C::kSwz);        // K as MN-major B (dQ)
@@ -152,217 +150,203 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const uint64_t dDO0_mn = tc::make_smem_desc(tc::smem_u32(sDO), C::kTileBytes, C::kSBO, C::kSwz);
       constexpr uint32_t kStageStep = C::kTileBytes >> 4, kHalfStep = (AB_SUB * C::kRowBytes) >> 4;
       constexpr uint32_t kKStepK = 32 >> 4, kKStepMN = (16 * C::kRowBytes) >> 4, kKStepDS = (16 * 128) >> 4;
-      auto issue_sdp = [&](int stage, int hh) {  // S^T = K Q_h^T ; dP^T = V dO_h^T   (h-th 64-row half of the tile)
-        const uint32_t off = stage * kStageStep + hh * kHalfStep;
+      constexpr uint32_t kDsBufStep = C::kDsBytes >> 4;
+      // sub-tile j -> (q tile j>>1, half j&1); its Q/dO ring stage is (j>>1) % AB_Q_STAGES, its fp32 stage is j&1
+      auto issue_sdp = [&](int j) {  // S^T = K Q_h^T ; dP^T = V dO_h^T into fp32 stage j&1
+        const int qstage = (j >> 1) % AB_Q_STAGES;
+        if ((j & 1) == 0) {  // first use of this Q/dO tile
+          tc::mbar_wait(&q_full[qstage], ((j >> 1) / AB_Q_STAGES) & 1);
+          tc::tcgen05_fence_after();
+        }
+        const uint32_t off = qstage * kStageStep + (j & 1) * kHalfStep;
+        const uint32_t tcol = tmem_base + (j & 1) * C::kStageCols;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          tc::mma_ss(tmem_base + C::kColST, dK_kmaj + k * kKStepK, dQ0_kmaj + off + k * kKStepK, idesc_st, k != 0);
+          tc::mma_ss(tcol + C::kColST, dK_kmaj + k * kKStepK, dQ0_kmaj + off + k * kKStepK, idesc_st, k != 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          tc::mma_ss(tmem_base + C::kColDPT, dV_kmaj + k * kKStepK, dDO0_kmaj + off + k * kKStepK, idesc_st, k != 0);
-        tc::mma_commit(sdp_full);
+          tc::mma_ss(tcol + C::kColDPT, dV_kmaj + k * kKStepK, dDO0_kmaj + off + k * kKStepK, idesc_st, k != 0);
+        tc::mma_commit(&sdp_full[j & 1]);
       };
       tc::mbar_wait(kv_full, 0);
-      tc::mbar_wait(&q_full[0], 0);
-      tc::tcgen05_fence_after();
-      issue_sdp(0, 0);
-      int stage = 0; uint32_t phase = 0;
+      issue_sdp(0);
+      if (n_sub > 1) issue_sdp(1);
       for (int i = 0; i < n_sub; ++i) {
-        const int m = i >> 1, hh = i & 1;
-        const uint32_t off = stage * kStageStep + hh * kHalfStep;
+        const int m = i >> 1, hh = i & 1, st = i & 1;
+        const int qstage = m % AB_Q_STAGES;
+        const uint32_t off = qstage * kStageStep + hh * kHalfStep;
+        const uint32_t tcol = tmem_base + st * C::kStageCols;
         AB_TRACE(0);
-        tc::mbar_wait(p_ready, i & 1);  // softmax(i) done: bf16 P^T / dS^T in TMEM, dS^T chunk hh in smem
+        tc::mbar_wait(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
         tc::tcgen05_fence_after();
         AB_TRACE(1);
 #pragma unroll
         for (int k = 0; k < AB_SUB / 16; ++k)  // dV += P^T dO_h
-          tc::mma_ts(tmem_base + C::kColDV, tmem_base + C::kColST + k * 8, dDO0_mn + off + k * kKStepMN, idesc_acc,
+          tc::mma_ts(tmem_base + C::kColDV, tcol + C::kColST + C::slice_off(k), dDO0_mn + off + k * kKStepMN, idesc_acc,
                      (i | k) != 0);
 #pragma unroll
         for (int k = 0; k < AB_SUB / 16; ++k)  // dK += dS^T Q_h
-          tc::mma_ts(tmem_base + C::kColDK, tmem_base + C::kColDPT + k * 8, dQ0_mn + off + k * kKStepMN, idesc_acc,
+          tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
                      (i | k) != 0);
         if (hh == 1) {
+          tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves was issued earlier)
           if (m > 0) {
             tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM
             tc::tcgen05_fence_after();
           }
+          const uint32_t dsoff = (m & 1) * kDsBufStep;
 #pragma unroll
           for (int k = 0; k < 128 / 16; ++k)  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
-            tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
+            tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + dsoff + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
           tc::mma_commit(dq_full);
         }
         AB_TRACE(2);
-        // scores of the next sub-tile (they overwrite P^T / dS^T in place: must follow their consumers in the MMA pipe)
-        if (i + 1 < n_sub) {
-          if (hh == 0) {
-            issue_sdp(stage, 1);
-          } else {
-            tc::mma_commit(&q_empty[stage]);  // Q_m / dO_m fully consumed
-            if (++stage == AB_Q_STAGES) { stage = 0; phase ^= 1; }
-            tc::mbar_wait(&q_full[stage], phase);
-            tc::tcgen05_fence_after();
-            issue_sdp(stage, 0);
-          }
-        }
+        // scores of sub-tile i+2 reuse fp32 stage st: queued behind the MMAs above, which read its bf16 contents
+        if (i + 2 < n_sub) issue_sdp(i + 2);
+        AB_TRACE(3);
       }
       tc::mma_commit(acc_full);
     }
     __syncwarp();
   } else {
-    // ===================== softmax-backward threads: thread <-> kv row, 64 query columns per sub-tile =============
-    const int quarter = warp & 3;
+    // ===================== softmax-backward threads: (kv row, 32 query columns) per sub-tile =====================
+    const int quarter = warp & 3, colhalf = warp >> 2;
     const int row = quarter * 32 + lane;  // kv row inside the tile == TMEM lane
-    const int tid = row;
+    const int tid = threadIdx.x;          // 0..255
     const bool kv_ok = (n0 + row) < p.S;
+    const bool partial_kv = (n0 + AB_T) > p.S;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const size_t bh = (size_t)b * p.H + h;
-    // per-query statistics of a q tile, fetched one tile ahead (raw values; transformed when stored)
-    auto ld_lse = [&](int m) { return p.lse[bh * p.S + min(m * AB_T + tid, p.S - 1)]; };
-    auto ld_delta = [&](int m) { return p.delta[bh * p.S + min(m * AB_T + tid, p.S - 1)]; };
-    float st_lse = ld_lse(0), st_delta = ld_delta(0);
-    for (int i = 0; i < n_sub; ++i) {
-      const int m = i >> 1, hh = i & 1;
-      const int slot = m & 1;
-      if (hh == 0) {
-        const bool ok = (m * AB_T + tid) < p.S;
-        sLse[slot * 128 + tid] = ok ? st_lse * kLog2e : INFINITY;
-        sDelta[slot * 128 + tid] = ok ? st_delta : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (m + 1 < n_q) { st_lse = ld_lse(m + 1); st_delta = ld_delta(m + 1); }
-      }
-      AB_TRACE(3);
-      tc::mbar_wait(sdp_full, i & 1);
+    // per-query statistics of a q tile, fetched one tile ahead (raw values; transformed when stored):
+    // threads 0..127 own lse, 128..255 own delta
+    auto ld_stat = [&](int m) {
+      const int qi = min(m * AB_T + (tid & 127), p.S - 1);
+      return (tid < 128) ? p.lse[bh * p.S + qi] : p.delta[bh * p.S + qi];
+    };
+    // TMEM -> registers -> swizzled smem tile -> ONE asynchronous bulk reduction into the fp32 accumulator
+    auto drain_dq = [&](int m) {
+      tc::mbar_wait(dq_full, m & 1);
       tc::tcgen05_fence_after();
-      AB_TRACE(4);
-      uint32_t s[2][32], dp[2][32];
-      tc::tmem_ld_x32(lane_addr + C::kColST, s[0]);
-      tc::tmem_ld_x32(lane_addr + C::kColST + 32, s[1]);
-      if (!(p.dbg & 4)) {
-        tc::tmem_ld_x32(lane_addr + C::kColDPT, dp[0]);
-        tc::tmem_ld_x32(lane_addr + C::kColDPT + 32, dp[1]);
+      uint32_t o[HD / 2];
+      if (HD == 32) {
+        uint32_t(&o16)[16] = reinterpret_cast<uint32_t(&)[16]>(o);
+        tc::tmem_ld_x16(lane_addr + C::kColDQ + colhalf * 16, o16);
       } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) { dp[0][q] = s[0][q]; dp[1][q] = s[1][q]; }
+        uint32_t(&o32)[32] = reinterpret_cast<uint32_t(&)[32]>(o);
+        tc::tmem_ld_x32(lane_addr + C::kColDQ + colhalf * 32, o32);
       }
       tc::tmem_ld_wait();
-      AB_TRACE(5);
-      auto compute = [&](auto partial_tag) {
-      constexpr bool kPartialKv = decltype(partial_tag)::value;
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(dq_free);  // dQ columns are in registers: the issuer may overwrite the TMEM tile
+      // the bulk reduction issued one query tile ago must have finished reading the staging buffer
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      uint8_t* srow = sDQ + row * (HD * 4);
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t pk[16], dk[16];
-        const float4* l4 = reinterpret_cast<const float4*>(sLse + slot * 128 + hh * AB_SUB + cc * 32);
-        const float4* d4 = reinterpret_cast<const float4*>(sDelta + slot * 128 + hh * AB_SUB + cc * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 lv = l4[q], dv = d4[q];
-          float p0 = fmaf(__uint_as_float(s[cc][4 * q]), p.scale_log2e, -lv.x);
-          float p1 = fmaf(__uint_as_float(s[cc][4 * q + 1]), p.scale_log2e, -lv.y);
-          float p2 = fmaf(__uint_as_float(s[cc][4 * q + 2]), p.scale_log2e, -lv.z);
-          float p3 = fmaf(__uint_as_float(s[cc][4 * q + 3]), p.scale_log2e, -lv.w);
-          if (!(p.dbg & 8)) { p0 = tc::fast_exp2(p0); p1 = tc::fast_exp2(p1); p2 = tc::fast_exp2(p2); p3 = tc::fast_exp2(p3); }
-          if (kPartialKv && !kv_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-          const float d0 = p0 * (__uint_as_float(dp[cc][4 * q]) - dv.x);
-          const float d1 = p1 * (__uint_as_float(dp[cc][4 * q + 1]) - dv.y);
-          const float d2 = p2 * (__uint_as_float(dp[cc][4 * q + 2]) - dv.z);
-          const float d3 = p3 * (__uint_as_float(dp[cc][4 * q + 3]) - dv.w);
-          pk[2 * q] = pack_bf16x2(p0, p1);
-          pk[2 * q + 1] = pack_bf16x2(p2, p3);
-          dk[2 * q] = pack_bf16x2(d0, d1);
-          dk[2 * q + 1] = pack_bf16x2(d2, d3);
-        }
-        // in place: all 64 fp32 columns of both buffers are already in registers
-        tc::tmem_st_x16(lane_addr + C::kColST + cc * 16, pk);    // P^T  (bf16 pairs): K-slices 2cc, 2cc+1
-        tc::tmem_st_x16(lane_addr + C::kColDPT + cc * 16, dk);   // dS^T (bf16 pairs)
-        // dS^T row -> smem (MN-major A operand of dQ = dS K): 64-query chunk hh, 16-byte pieces cc*4 .. +3
-        uint8_t* rowp = sDS + hh * (128 * 128) + row * 128;
-        if (!(p.dbg & 2))
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int piece = cc * 4 + q;
-          uint4 v = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
-          *reinterpret_cast<uint4*>(rowp + ((piece ^ (row & 7)) << 4)) = v;
-        }
+      for (int q = 0; q < HD / 8; ++q) {  // 16-byte chunk j of this row lands at chunk (j & 8) | ((j ^ row) & 7)
+        const int j = colhalf * (HD / 8) + q;
+        const int pos = (j & 8) | ((j ^ row) & 7);
+        *reinterpret_cast<uint4*>(srow + pos * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       }
-      };
-      // the last kv tile of a sequence has rows past S (zero K rows would still give p = exp2(-lse) != 0): mask them there only
-      if (n0 + AB_T <= p.S) compute(std::false_type{}); else compute(std::true_type{});
+      tc::fence_proxy_async();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (tid == 0) {
+        float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                     "r"(tc::smem_u32(sDQ)), "r"((uint32_t)C::kDqBytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    float stat = ld_stat(0);
+    for (int i = 0; i < n_sub; ++i) {
+      const int m = i >> 1, hh = i & 1, st = i & 1;
+      const int slot = m & 1;
+      if (hh == 0) {
+        const bool ok = (m * AB_T + (tid & 127)) < p.S;
+        if (tid < 128) sLse[slot * 128 + tid] = ok ? stat * kLog2e : INFINITY;
+        else sDelta[slot * 128 + (tid & 127)] = ok ? stat : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (m + 1 < n_q) stat = ld_stat(m + 1);
+      }
+      const uint32_t tcol = lane_addr + st * C::kStageCols + colhalf * 32;
+      AB_TRACE(4);
+      tc::mbar_wait(&sdp_full[st], (i >> 1) & 1);
+      tc::tcgen05_fence_after();
+      AB_TRACE(5);
+      uint32_t s[32], dp[32];
+      tc::tmem_ld_x32(tcol + C::kColST, s);
+      tc::tmem_ld_x32(tcol + C::kColDPT, dp);
+      tc::tmem_ld_wait();
       AB_TRACE(6);
+      uint32_t pk[16], dk[16];
+      const float4* l4 = reinterpret_cast<const float4*>(sLse + slot * 128 + hh * AB_SUB + colhalf * 32);
+      const float4* d4 = reinterpret_cast<const float4*>(sDelta + slot * 128 + hh * AB_SUB + colhalf * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 lv = l4[q], dv = d4[q];
+        float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q]), p.scale_log2e, -lv.x));
+        float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q + 1]), p.scale_log2e, -lv.y));
+        float p2 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q + 2]), p.scale_log2e, -lv.z));
+        float p3 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q + 3]), p.scale_log2e, -lv.w));
+        // rows past S exist only in the last kv tile (zero K rows would still give p = exp2(-lse) != 0)
+        if (partial_kv && !kv_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+        const float d0 = p0 * (__uint_as_float(dp[4 * q]) - dv.x);
+        const float d1 = p1 * (__uint_as_float(dp[4 * q + 1]) - dv.y);
+        const float d2 = p2 * (__uint_as_float(dp[4 * q + 2]) - dv.z);
+        const float d3 = p3 * (__uint_as_float(dp[4 * q + 3]) - dv.w);
+        pk[2 * q] = pack_bf16x2(p0, p1);
+        pk[2 * q + 1] = pack_bf16x2(p2, p3);
+        dk[2 * q] = pack_bf16x2(d0, d1);
+        dk[2 * q + 1] = pack_bf16x2(d2, d3);
+      }
+      // in place: this thread's 32 fp32 columns of both buffers are in registers; its bf16 output reuses their first 16
+      tc::tmem_st_x16(tcol + C::kColST, pk);    // P^T  (bf16 pairs): K-slices 2 colhalf, 2 colhalf + 1
+      tc::tmem_st_x16(tcol + C::kColDPT, dk);   // dS^T (bf16 pairs)
+      // dS^T row -> smem (MN-major A operand of dQ = dS K): buffer m&1, 64-query chunk hh, 16-byte pieces 4 colhalf .. +3
+      uint8_t* rowp = sDS + (m & 1) * C::kDsBytes + hh * (128 * 128) + row * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int piece = colhalf * 4 + q;
+        *reinterpret_cast<uint4*>(rowp + ((piece ^ (row & 7)) << 4)) = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+      }
+      AB_TRACE(7);
       tc::tmem_st_wait();
       tc::fence_proxy_async();  // st.shared (generic proxy) -> tcgen05.mma reads (async proxy)
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(p_ready);
-      AB_TRACE(7);
-      if (hh == 1) {
-        // drain dQ_m and reduce it into the fp32 accumulator (TMEM lane = query row here)
-        tc::mbar_wait(dq_full, m & 1);
-        tc::tcgen05_fence_after();
-        AB_TRACE(8);
-        // TMEM -> registers -> swizzled smem tile -> ONE asynchronous bulk reduction (cp.reduce.async.bulk .add.f32) into
-        // the fp32 accumulator; per-thread red.global instructions kept the softmax threads busy for ~3000 cycles
-        uint8_t* srow = sDQ + row * (HD * 4);
-        // the bulk reduction issued one query tile ago must have finished reading the staging buffer
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t o[32];
-          tc::tmem_ld_x32(lane_addr + C::kColDQ + c * 32, o);
-          tc::tmem_ld_wait();
-          if (c == HD / 32 - 1) {  // dQ columns are in registers: the issuer may overwrite the TMEM tile
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(dq_free);
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {  // 16-byte chunk j = c*8 + q of this row lands at chunk (j&8) | ((j ^ row) & 7)
-            const int pos = c * 8 + ((q ^ row) & 7);
-            *reinterpret_cast<uint4*>(srow + pos * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          }
-        }
-        tc::fence_proxy_async();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (tid == 0 && !(p.dbg & 1)) {
-          float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD;
-          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                       "r"(tc::smem_u32(sDQ)), "r"((uint32_t)C::kDqBytes)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        AB_TRACE(9);
-      }
+      tc::mbar_arrive(&p_ready[st]);
+      AB_TRACE(8);
+      // deferred drain: dQ of the previous query tile was queued a full sub-tile ago
+      if (hh == 0 && m > 0) drain_dq(m - 1);
+      AB_TRACE(9);
     }
-    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0) {
-      for (int i = 0; i < 4; ++i)
-        for (int k = 0; k < 10; ++k) printf("TRACE i%d id%d %lld\n", i + 4, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
-    }
+    drain_dq(n_q - 1);
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    // epilogue: dV, dK of this kv tile
+    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
+      for (int i = 0; i < 8; ++i)
+        for (int k = 0; k < 10; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
+    }
+    // epilogue: column half 0 stores dV, half 1 stores dK of this kv tile
     tc::mbar_wait(acc_full, 0);
     tc::tcgen05_fence_after();
     const int kv = n0 + row;
-    __nv_bfloat16* dk_row = p.dqkv + ((((size_t)b * p.S + kv) * 3 + 1) * p.H + h) * HD;
-    __nv_bfloat16* dv_row = dk_row + (size_t)p.H * HD;
+    const uint32_t col = colhalf ? C::kColDK : C::kColDV;
+    const float sc = colhalf ? p.scale : 1.f;
+    __nv_bfloat16* dst = p.dqkv + ((((size_t)b * p.S + kv) * 3 + (colhalf ? 1 : 2)) * p.H + h) * HD;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t col = which ? C::kColDK : C::kColDV;
-      const float sc = which ? p.scale : 1.f;
-      __nv_bfloat16* dst = which ? dk_row : dv_row;
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld_x32(lane_addr + col + c * 32, o);
+      tc::tmem_ld_wait();
+      if (kv_ok) {
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t o[32];
-        tc::tmem_ld_x32(lane_addr + col + c * 32, o);
-        tc::tmem_ld_wait();
-        if (kv_ok) {
-#pragma unroll
-          for (int q = 0; q < 32; q += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[q]) * sc, __uint_as_float(o[q + 1]) * sc);
-            v.y = pack_bf16x2(__uint_as_float(o[q + 2]) * sc, __uint_as_float(o[q + 3]) * sc);
-            v.z = pack_bf16x2(__uint_as_float(o[q + 4]) * sc, __uint_as_float(o[q + 5]) * sc);
-            v.w = pack_bf16x2(__uint_as_float(o[q + 6]) * sc, __uint_as_float(o[q + 7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c * 32 + q) = v;
-          }
+        for (int q = 0; q < 32; q += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[q]) * sc, __uint_as_float(o[q + 1]) * sc);
+          v.y = pack_bf16x2(__uint_as_float(o[q + 2]) * sc, __uint_as_float(o[q + 3]) * sc);
+          v.z = pack_bf16x2(__uint_as_float(o[q + 4]) * sc, __uint_as_float(o[q + 5]) * sc);
+          v.w = pack_bf16x2(__uint_as_float(o[q + 6]) * sc, __uint_as_float(o[q + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + c * 32 + q) = v;
         }
       }
     }
@@ -370,9 +354,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc::tcgen05_fence_after();
-    tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+    tc::tmem_dealloc<512>(tmem_base);
   }
 }
 

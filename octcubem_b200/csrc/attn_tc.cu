@@ -50,29 +50,27 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 template <int HD, bool kMasked>
 __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, uint64_t* o_done, int j, int valid,
                                              float scale_log2e, float& m, float& l) {
-  // pass 1: row maximum of the raw scores (TMEM reads are cheap; keeping 128 scores live would cost 128 registers).
-  // Chunk c+1 is requested before chunk c is consumed (register double buffer) so the TMEM latency stays hidden.
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-  uint32_t sr[2][32];
-  tc::tmem_ld_x32(tmem_s, sr[0]);
-  tc::tmem_ld_wait();
+  // Single pass over TMEM: the whole 128-column score row is held in registers (tcgen05.ld runs at ~64 B/clk/SM, so
+  // reading S twice — once for the maximum, once for the exponentials — made the kernel TMEM-load-bound).
+  uint32_t sr[4][32];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
-    uint32_t(&cur)[32] = sr[c & 1];
-    if (kMasked) {
+  for (int c = 0; c < 4; ++c) tc::tmem_ld_x32(tmem_s + c * 32, sr[c]);
+  tc::tmem_ld_wait();
+  if (kMasked) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (c * 32 + i >= valid) cur[i] = 0xff800000u;  // -inf
-    }
+        if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      mx0 = max3(mx0, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
-      mx1 = max3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+      mx0 = max3(mx0, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+      mx1 = max3(mx1, __uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3]));
     }
-    if (c < 3) tc::tmem_ld_wait();
-  }
-  tc::tmem_ld_x32(tmem_s, sr[0]);  // first chunk of pass 2, in flight during the rescale decision
   const float m_tile = fmaxf(mx0, mx1) * scale_log2e;
   const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
   if (__any_sync(0xffffffffu, need)) {
@@ -82,45 +80,34 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
       tc::mbar_wait(o_done, (j - 1) & 1);  // O += P(j-1) V_{j-1} has landed
       tc::tcgen05_fence_after();
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t o[32];
-        tc::tmem_ld_x32(tmem_o + c * 32, o);
+      for (int c = 0; c < HD / 16; ++c) {
+        uint32_t o[16];
+        tc::tmem_ld_x16(tmem_o + c * 16, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-        tc::tmem_st_x32(tmem_o + c * 32, o);
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+        tc::tmem_st_x16(tmem_o + c * 16, o);
       }
       l *= factor;
     }
     m = m_new;
   }
-  // pass 2: P = exp2(s * c - m) as bf16 pairs written over the consumed part of S (chunk c occupies columns
-  // [16c, 16c+16) while the unread chunks start at 32(c+1), so the in-place overwrite never races ahead)
+  // P = exp2(s * c - m) as bf16 pairs written over S (masked columns hold -inf -> exactly 0)
   float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-  tc::tmem_ld_wait();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (c < 3) tc::tmem_ld_x32(tmem_s + (c + 1) * 32, sr[(c + 1) & 1]);
-    uint32_t(&cur)[32] = sr[c & 1];
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-      float p0 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i]), scale_log2e, -m));
-      float p1 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), scale_log2e, -m));
-      float p2 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 2]), scale_log2e, -m));
-      float p3 = tc::fast_exp2(fmaf(__uint_as_float(cur[2 * i + 3]), scale_log2e, -m));
-      if (kMasked) {
-        if (c * 32 + 2 * i >= valid) p0 = 0.f;
-        if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-        if (c * 32 + 2 * i + 2 >= valid) p2 = 0.f;
-        if (c * 32 + 2 * i + 3 >= valid) p3 = 0.f;
-      }
+      const float p0 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i]), scale_log2e, -m));
+      const float p1 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i + 1]), scale_log2e, -m));
+      const float p2 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i + 2]), scale_log2e, -m));
+      const float p3 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i + 3]), scale_log2e, -m));
       l0 += p0; l1 += p1; l2 += p2; l3 += p3;
       pk[i] = pack_bf16x2(p0, p1);
       pk[i + 1] = pack_bf16x2(p2, p3);
     }
-    if (c < 3) tc::tmem_ld_wait();         // chunk c+1 is in registers before chunk c's columns are overwritten
-    tc::tmem_st_x16(tmem_s + c * 16, pk);  // in place: bf16 chunk c -> columns [16c,16c+16), all read already
+    tc::tmem_st_x16(tmem_s + c * 16, pk);
   }
   l += (l0 + l1) + (l2 + l3);
 }
