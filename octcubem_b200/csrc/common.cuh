@@ -76,6 +76,27 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Fast erf for the tensor-core epilogues (Abramowitz & Stegun 7.1.26, |abs err| < 1.5e-7 — two orders of magnitude
+// below bf16 rounding): 2 SFU ops + ~10 FMAs instead of erff's ~30 instructions.  The fp32 parity path keeps erff.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = __expf(-ax * ax);
+  const float r = fmaf(-poly, e, 1.f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
 // generic typed load/store to float
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }

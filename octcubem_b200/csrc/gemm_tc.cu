@@ -3,8 +3,8 @@
 // nn.Linear forward (flash_attn/modules/mha.py:635,703, mlp.py:48-50, models_mae_joint_res_flash_attn.py:511,595)
 // and their autograd dgrad / wgrad.
 //
-// Persistent, warp-specialised CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator),
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Two TMEM accumulator stages let the epilogue of tile i
+// Persistent, warp-specialised CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator),
+// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the columns).  Two TMEM accumulator stages let the epilogue of tile i
 // overlap the main loop of tile i+1.
 //
 // Operand layouts (all row-major in global memory):
@@ -13,6 +13,7 @@
 //   NT: A K-major,  B K-major      NN: A K-major, B MN-major      TN: A MN-major, B MN-major
 #include "tc_common.cuh"
 #include <mutex>
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------
 // host: driver entry point + tensor map helper
@@ -58,8 +59,11 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle line
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr int kGroupM = 8;    // tile rasterisation: groups of 8 m-blocks sweep all n-blocks (L2 reuse of both operands)
+
+constexpr int kEpiStageBytes = 128 * 128;  // one [128 rows x 128 B] output group per column half
 
 template <int BLOCK_N>
 struct Cfg {
@@ -68,7 +72,7 @@ struct Cfg {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -80,13 +84,21 @@ struct GemmParams {
   const float* bias;
   void* aux;
   int beta;
+  int dbg;           // OCT_GEMM_DBG timing experiments (0 in production): 1 = epilogue skips its global stores
   int splits;        // split-K factor (fp32 D, EPI_NONE only): partial products are reduced with red.global.add
   int kb_per_split;  // k-blocks per split
 };
 
-template <bool A_MN, bool B_MN, int BLOCK_N>
+// kPair: the grid is launched in clusters of two CTAs that work on vertically adjacent 128-row tiles of the same
+// 256-column strip.  Each CTA fetches only HALF of the shared B tile and TMA-multicasts it into both CTAs' smem, so the
+// L2 -> SM operand traffic per MMA drops from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2-bandwidth-bound at
+// ~26 TB/s demand, profiles/r1_gemm_ncu.md).  A stage may only be refilled once BOTH CTAs' MMAs have consumed it,
+// hence the multicast tcgen05.commit onto both empty barriers (arrival count 2).
+template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                               const __grid_constant__ CUtensorMap tmap_b,
+                                                              const __grid_constant__ CUtensorMap tmap_d,
+                                                              const __grid_constant__ CUtensorMap tmap_aux,
                                                               const GemmParams p) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -94,7 +106,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // 2 x 16 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 2 * kEpiStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -102,7 +115,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M, num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int rank = kPair ? (int)tc::cluster_ctarank() : 0;
+  const int cta = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // index of this CTA (pair) in the work loop
+  const int ncta = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // tile rows are handed out in units of one m-block (two vertically adjacent m-blocks for a pair)
+  const int num_m = kPair ? (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_work = num_tiles * p.splits;  // work item w: tile = w % num_tiles, split = w / num_tiles
@@ -110,19 +128,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
     tc::prefetch_tmap(&tmap_b);
+    tc::prefetch_tmap(&tmap_d);
     for (int s = 0; s < C::kStages; ++s) {
       tc::mbar_init(&full_bar[s], 1);
-      tc::mbar_init(&empty_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], kPair ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tmem_full[s], 1);
-      tc::mbar_init(&tmem_empty[s], 128);
+      tc::mbar_init(&tmem_empty[s], kEpiThreads);
     }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_base_slot);
   tc::tcgen05_fence_before();
   __syncthreads();
+  if (kPair) tc::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -131,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int g = t / per_group, first_m = g * kGroupM;
     const int gsz = min(num_m - first_m, kGroupM);
     m_blk = first_m + (t % per_group) % gsz;
+    if (kPair) m_blk = 2 * m_blk + rank;  // may point one block past M for the odd tail: TMA zero-fills, stores are masked
     n_blk = (t % per_group) / gsz;
   };
 
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = cta; w < num_work; w += ncta) {
         int m_blk, n_blk;
         tile_coords(w % num_tiles, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
@@ -157,12 +178,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int c = 0; c < BLOCK_M / 64; ++c)
               tc::tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + c * 64, k0);
           }
-          if (!B_MN) {
-            tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
-          } else {
+          if (!kPair) {
+            if (!B_MN) {
+              tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              tc::tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0);
+              for (int c = 0; c < BLOCK_N / 64; ++c)
+                tc::tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0);
+            }
+          } else {  // my half of the B tile, delivered to both CTAs of the pair
+            if (!B_MN) {
+              tc::tma_load_2d_mc(sb + rank * (BLOCK_N / 2) * 128, &tmap_b, &full_bar[stage], k0, n0 + rank * (BLOCK_N / 2), 3);
+            } else {
+#pragma unroll
+              for (int cc = 0; cc < BLOCK_N / 128; ++cc) {
+                const int c = rank * (BLOCK_N / 128) + cc;
+                tc::tma_load_2d_mc(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0, 3);
+              }
+            }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -175,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = cta; w < num_work; w += ncta) {
       if (lane == 0) {
         tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc::tcgen05_fence_after();
@@ -195,7 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                      : tc::make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
             tc::mma_ss(tmem_d, da, db, idesc, (kb | k) != 0);
           }
-          tc::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (in both CTAs of a pair: the peer multicasts into it)
+          if (kPair) tc::mma_commit_mc(&empty_bar[stage], 3); else tc::mma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         tc::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -204,124 +238,185 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps share a TMEM lane quarter and split the tile's columns.  Results leave the SM through a swizzled smem
+    // staging tile and ONE TMA store per 128-byte-wide column group: per-lane global stores (32 different rows per warp
+    // instruction) made output-heavy GEMMs store-bound — 70 us with, 38 us without them at 32776x1536x512
+    // (profiles/r1_gemm_ncu.md).  fp32 accumulate / split-K partials use the reducing store (cp.reduce ... .add).
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    const int colhalf = (warp - 2) >> 2;
+    const int tile_row = quarter * 32 + lane;
+    uint8_t* stg = smem_epi + colhalf * kEpiStageBytes;
+    uint8_t* stg_row = stg + tile_row * 128;
+    const uint32_t stg_addr = tc::smem_u32(stg);
+    const int bar_id = 1 + colhalf;
+    const bool issuer = (quarter == 0) && (lane == 0);
+    // 128-byte row segment (32 x 32-bit) -> staging tile -> TMA store of the [128 rows x 128 B] group at (col, row0)
+    auto stage_and_store = [&](const uint32_t (&o)[32], const CUtensorMap* map, int col, int row0, bool reduce_add) {
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(stg_row + ((q ^ (tile_row & 7)) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      tc::fence_proxy_async();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (issuer && !(p.dbg & 1)) {
+        if (reduce_add)
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(map)), "r"(stg_addr), "r"(col), "r"(row0) : "memory");
+        else
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(map)), "r"(stg_addr), "r"(col), "r"(row0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = cta; w < num_work; w += ncta) {
       int m_blk, n_blk;
       tile_coords(w % num_tiles, m_blk, n_blk);
-      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const int row0 = m_blk * BLOCK_M;
+      const int row = row0 + tile_row;
       const int n0 = n_blk * BLOCK_N;
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      if (p.d_bf16) {
+        constexpr int kGroups = BLOCK_N / 128;  // 64-column (128-byte) groups per column half
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-        const int nc = n0 + ch * 32;
-        if (nc >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tc::tmem_ld_x32(taddr + ch * 32, r);
-        tc::tmem_ld_wait();
-        if (row < p.M) {
-          float v[32];
+        for (int gg = 0; gg < kGroups; ++gg) {
+          const int g = colhalf * kGroups + gg;
+          const int nc = n0 + g * 64;
+          if (nc >= p.N) break;  // uniform over the 128 threads of this column half
+          uint32_t r0[32], r1[32];
+          tc::tmem_ld_x32(taddr + g * 64, r0);
+          tc::tmem_ld_x32(taddr + g * 64 + 32, r1);
+          tc::tmem_ld_wait();
+          if (gg == kGroups - 1 || nc + 64 >= p.N) {  // last TMEM read of this tile: hand the accumulator back
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&tmem_empty[acc]);
+          }
+          float v[64];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          const int nvalid = min(32, p.N - nc);  // multiple of 8 (N % 8 == 0)
+          for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
           if (p.epilogue == OCT_EPI_BIAS || p.epilogue == OCT_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (i < nvalid) {
+            for (int i = 0; i < 64; i += 4) {
+              if (nc + i < p.N) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + i));
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
             }
           }
-          const size_t off = (size_t)row * p.ldd + nc;
-          if (p.d_bf16) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
-            __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(p.aux) + off;
+          uint32_t o[32];
+          if (p.epilogue == OCT_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < nvalid) {
-                if (p.epilogue == OCT_EPI_BIAS_GELU) {
-                  uint4 pre;
-                  pre.x = pack_bf16x2(v[i], v[i + 1]); pre.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                  pre.z = pack_bf16x2(v[i + 4], v[i + 5]); pre.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                  *reinterpret_cast<uint4*>(ax + i) = pre;
-                  // GELU is evaluated on the bf16-rounded pre-activation, like nn.GELU on a bf16 tensor
+            for (int i = 0; i < 32; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            stage_and_store(o, &tmap_aux, nc, row0, false);  // pre-activation
+            // GELU is evaluated on the bf16-rounded pre-activation, like nn.GELU on a bf16 tensor
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[i + j] = gelu_erf(bf16_round(v[i + j]));
-                } else if (p.epilogue == OCT_EPI_DGELU) {
+            for (int i = 0; i < 64; ++i) v[i] = gelu_fast(bf16_round(v[i]));
+          } else if (p.epilogue == OCT_EPI_DGELU) {
+            if (row < p.M) {
+              const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + nc;
+#pragma unroll
+              for (int i = 0; i < 64; i += 8) {
+                if (nc + i < p.N) {
                   const uint4 pre = *reinterpret_cast<const uint4*>(ax + i);
                   const float2 a0 = unpack_bf16x2(pre.x), a1 = unpack_bf16x2(pre.y), a2 = unpack_bf16x2(pre.z),
                                a3 = unpack_bf16x2(pre.w);
-                  v[i] *= gelu_erf_grad(a0.x); v[i + 1] *= gelu_erf_grad(a0.y);
-                  v[i + 2] *= gelu_erf_grad(a1.x); v[i + 3] *= gelu_erf_grad(a1.y);
-                  v[i + 4] *= gelu_erf_grad(a2.x); v[i + 5] *= gelu_erf_grad(a2.y);
-                  v[i + 6] *= gelu_erf_grad(a3.x); v[i + 7] *= gelu_erf_grad(a3.y);
+                  v[i] *= gelu_fast_grad(a0.x); v[i + 1] *= gelu_fast_grad(a0.y);
+                  v[i + 2] *= gelu_fast_grad(a1.x); v[i + 3] *= gelu_fast_grad(a1.y);
+                  v[i + 4] *= gelu_fast_grad(a2.x); v[i + 5] *= gelu_fast_grad(a2.y);
+                  v[i + 6] *= gelu_fast_grad(a3.x); v[i + 7] *= gelu_fast_grad(a3.y);
                 }
-                uint4 o;
-                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(d + i) = o;
-              }
-            }
-          } else {
-            float* d = reinterpret_cast<float*>(p.D) + off;
-            float* ax = reinterpret_cast<float*>(p.aux) + off;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (i < nvalid) {
-                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (p.epilogue == OCT_EPI_BIAS_GELU) {
-                  *reinterpret_cast<float4*>(ax + i) = o;
-                  o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
-                } else if (p.epilogue == OCT_EPI_DGELU) {
-                  const float4 a = *reinterpret_cast<const float4*>(ax + i);
-                  o.x *= gelu_erf_grad(a.x); o.y *= gelu_erf_grad(a.y); o.z *= gelu_erf_grad(a.z); o.w *= gelu_erf_grad(a.w);
-                } else if (p.splits > 1) {  // split-K partial: reduce in L2 (D was zeroed, or holds beta*D)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + i), "f"(o.x), "f"(o.y),
-                               "f"(o.z), "f"(o.w) : "memory");
-                  continue;
-                } else if (p.beta) {
-                  const float4 a = *reinterpret_cast<const float4*>(d + i);
-                  o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                }
-                *reinterpret_cast<float4*>(d + i) = o;
               }
             }
           }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          stage_and_store(o, &tmap_d, nc, row0, false);
+        }
+      } else {
+        constexpr int kGroups = BLOCK_N / 64;  // 32-column (128-byte) fp32 groups per column half
+#pragma unroll 1
+        for (int gg = 0; gg < kGroups; ++gg) {
+          const int g = colhalf * kGroups + gg;
+          const int nc = n0 + g * 32;
+          if (nc >= p.N) break;
+          uint32_t o[32];
+          tc::tmem_ld_x32(taddr + g * 32, o);
+          tc::tmem_ld_wait();
+          if (gg == kGroups - 1 || nc + 32 >= p.N) {
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&tmem_empty[acc]);
+          }
+          if (p.epilogue == OCT_EPI_BIAS) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (nc + i < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + i));
+                o[i] = __float_as_uint(__uint_as_float(o[i]) + b4.x);
+                o[i + 1] = __float_as_uint(__uint_as_float(o[i + 1]) + b4.y);
+                o[i + 2] = __float_as_uint(__uint_as_float(o[i + 2]) + b4.z);
+                o[i + 3] = __float_as_uint(__uint_as_float(o[i + 3]) + b4.w);
+              }
+            }
+          }
+          // beta = 1 and split-K partial products accumulate in L2 through the reducing TMA store
+          stage_and_store(o, &tmap_d, nc, row0, p.beta != 0 || p.splits > 1);
         }
       }
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&tmem_empty[acc]);
+      // a tile whose column half lies entirely beyond N never reached an arrive above
+      if (n0 + colhalf * (BLOCK_N / 2) >= p.N) {
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have left smem and are visible
   }
 
   tc::tcgen05_fence_before();
   __syncthreads();
+  if (kPair) tc::cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc::tcgen05_fence_after();
     tc::tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
-template <bool A_MN, bool B_MN, int BLOCK_N>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx, const GemmParams& p,
+           cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
-  auto kern = gemm_tc_kernel<A_MN, B_MN, BLOCK_N>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, BLOCK_N, kPair>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  const int num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int unit_m = kPair ? 2 * BLOCK_M : BLOCK_M;
+  const int num_tiles = ((p.M + unit_m - 1) / unit_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int num_work = num_tiles * p.splits;
-  const int grid = num_work < oct_num_sms() ? num_work : oct_num_sms();
-  kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, p);
+  if (!kPair) {
+    const int grid = num_work < oct_num_sms() ? num_work : oct_num_sms();
+    kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, td, tx, p);
+  } else {
+    const int pairs = oct_num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (num_work < pairs ? num_work : pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, p);
+    if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): cluster launch: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   return oct_check_launch("oct_gemm(bf16)");
 }
 
@@ -358,17 +453,38 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   CUtensorMap ta, tb;
   int rc = make_operand_map(&ta, A, a_mn, M, K, lda, BLOCK_M, "oct_gemm(bf16) A");
   if (rc) return rc;
-  rc = make_operand_map(&tb, B, b_mn, N, K, ldb, block_n, "oct_gemm(bf16) B");
+  // pair mode (2-CTA clusters sharing B through TMA multicast) whenever there are at least two m-blocks
+  const bool pair = (M > BLOCK_M) && (getenv("OCT_GEMM_NO_PAIR") == nullptr);
+  rc = make_operand_map(&tb, B, b_mn, N, K, ldb, pair ? block_n / 2 : block_n, "oct_gemm(bf16) B");
   if (rc) return rc;
+  // output maps for the TMA-store epilogue: [M, N] row-major, one box = 128 rows x 128 bytes
+  OCT_REQUIRE(d_dtype == OCT_BF16 || (epilogue != OCT_EPI_BIAS_GELU && epilogue != OCT_EPI_DGELU),
+              "oct_gemm(bf16): GELU epilogues need a bf16 D");
+  CUtensorMap td, tx;
+  {
+    const bool f32 = (d_dtype == OCT_F32);
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)ldd * (f32 ? 4 : 2)};
+    uint32_t box[2] = {f32 ? 32u : 64u, (uint32_t)BLOCK_M};
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    rc = oct_make_tmap(&td, dt, 2, D, dims, strides, box, "oct_gemm(bf16) D");
+    if (rc) return rc;
+    tx = td;
+    if (epilogue == OCT_EPI_BIAS_GELU) {
+      rc = oct_make_tmap(&tx, dt, 2, aux, dims, strides, box, "oct_gemm(bf16) aux");
+      if (rc) return rc;
+    }
+  }
   GemmParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.ldd = ldd; p.D = D; p.d_bf16 = (d_dtype == OCT_BF16);
   p.epilogue = epilogue; p.bias = bias; p.aux = aux; p.beta = beta;
+  { const char* e = getenv("OCT_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   // split-K: wgrad-shaped problems (few output tiles, long contraction) would otherwise occupy a fraction of the chip
   p.splits = 1;
   const int num_kb = (int)ceil_div64(K, BLOCK_K);
   p.kb_per_split = num_kb;
   if (d_dtype == OCT_F32 && epilogue == OCT_EPI_NONE) {
-    const int64_t tiles = ceil_div64(M, BLOCK_M) * ceil_div64(N, block_n);
+    const int64_t tiles = ceil_div64(M, pair ? 2 * BLOCK_M : BLOCK_M) * ceil_div64(N, block_n) * (pair ? 2 : 1);
     const int sms = oct_num_sms();
     if (tiles * 2 <= sms && num_kb >= 16) {
       int splits = (int)(sms / tiles);
@@ -383,8 +499,9 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
       }
     }
   }
-#define GO(AMN, BMN)                                                                    \
-  return block_n == 256 ? launch<AMN, BMN, 256>(ta, tb, p, st) : launch<AMN, BMN, 128>(ta, tb, p, st)
+#define GO(AMN, BMN)                                                                                         \
+  if (pair) return block_n == 256 ? launch<AMN, BMN, 256, true>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, true>(ta, tb, td, tx, p, st); \
+  return block_n == 256 ? launch<AMN, BMN, 256, false>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, false>(ta, tb, td, tx, p, st)
   switch (layout) {
     case OCT_GEMM_NT: GO(false, false);
     case OCT_GEMM_NN: GO(false, true);
