@@ -161,8 +161,8 @@ def main_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")  # NCCL prints its version banner on stdout at these levels; keep stdout = one JSON line
     threading.Thread(target=_watchdog, args=(1500,), daemon=True).start()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
