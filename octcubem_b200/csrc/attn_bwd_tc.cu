@@ -360,28 +360,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   }
 }
 
-// delta[b,h,s] = sum_c dO[b,s,h,c] * O[b,s,h,c]   (one warp per (b,s,h))
+// delta[b,h,s] = sum_c dO[b,s,h,c] * O[b,s,h,c]   (one thread per (b,s,h) row: HD bf16 = 64 / 128 contiguous bytes)
 template <int HD>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                   float* __restrict__ delta, int64_t total, int S, int H) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= total) return;
-  const int64_t base = w * HD;
+  const uint4* a = reinterpret_cast<const uint4*>(out + w * HD);
+  const uint4* d = reinterpret_cast<const uint4*>(dout + w * HD);
   float acc = 0.f;
-  if (lane * 2 < HD) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(out + base + lane * 2));
-    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + base + lane * 2));
-    acc = a.x * d.x + a.y * d.y;
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    const uint4 x = a[i], y = d[i];
+    const float2 x0 = unpack_bf16x2(x.x), x1 = unpack_bf16x2(x.y), x2 = unpack_bf16x2(x.z), x3 = unpack_bf16x2(x.w);
+    const float2 y0 = unpack_bf16x2(y.x), y1 = unpack_bf16x2(y.y), y2 = unpack_bf16x2(y.z), y3 = unpack_bf16x2(y.w);
+    acc += (x0.x * y0.x + x0.y * y0.y) + (x1.x * y1.x + x1.y * y1.y) + (x2.x * y2.x + x2.y * y2.y) +
+           (x3.x * y3.x + x3.y * y3.y);
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const int hh = (int)(w % H);
-    const int64_t bs = w / H;
-    const int s = (int)(bs % S);
-    const int64_t bb = bs / S;
-    delta[(bb * H + hh) * S + s] = acc;
-  }
+  const int hh = (int)(w % H);
+  const int64_t bs = w / H;
+  const int s = (int)(bs % S);
+  const int64_t bb = bs / S;
+  delta[(bb * H + hh) * S + s] = acc;
 }
 
 // dq (bf16, into dqkv[:, :, 0]) = scale * dq_acc
@@ -425,7 +425,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * H * Spad * HD * sizeof(float), st);
   if (e != cudaSuccess) { oct_set_error("oct_attn_bwd(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
   const int64_t rows = B * S * H;
-  attn_delta_kernel<HD><<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>((const __nv_bfloat16*)out,
+  attn_delta_kernel<HD><<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>((const __nv_bfloat16*)out,
                                                                               (const __nv_bfloat16*)dout, delta, rows,
                                                                               (int)S, (int)H);
   rc = oct_check_launch("oct_attn_bwd(bf16,delta)");

@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(1024) ln_bwd_finish_kernel(const float* __rest
 }
 
 static int64_t ln_bwd_blocks(int64_t M) {
-  int64_t blocks = ceil_div64(M, kLnWarps);
-  const int64_t cap = (int64_t)oct_num_sms() * 4;
+  int64_t blocks = ceil_div64(M, (int64_t)kLnWarps);  // one row per warp when M is small: the kernel is latency-bound there
+  const int64_t cap = (int64_t)oct_num_sms() * 8;
   return blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
 }
 
