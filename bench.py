@@ -322,29 +322,51 @@ def main_b200(args):
 
 
 def dominant_kernel_roofline(ops, dev, pk):
-    """Decoder attention backward (B=8, S=4097, 16 heads x 32): the largest single share of the step (profiles/)."""
-    from octcubem_b200._lib import OCT_BF16
+    """Decoder attention backward (B=8, S=4097, 16 heads x 32): the largest single share of the step
+    (profiles/r1_step_launches.md), timed alone with CUDA events on the launching stream.  `achieved` counts the
+    ALGORITHMIC FLOPs of SURVEY §8d (bwd = 2 x 4 S^2 dim, no recompute); the same object also reports the kernel
+    against its SFU (ex2) bound, which is the tighter roofline for head_dim 32."""
+    from octcubem_b200._lib import EPI_BIAS, GEMM_NT, OCT_BF16
     B, S, H, d = BATCH, (FRAMES // 3) * 256 + 1, 16, 32
     qkv = (torch.randn(B, S, 3 * H * d, device=dev) * 0.5).bfloat16()
     dout = torch.randn(B, S, H * d, device=dev).bfloat16()
     out, lse = ops.attn_fwd(qkv, H, d, OCT_BF16)
-    for _ in range(3):
-        ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16)
-    torch.cuda.synchronize()
-    n = 10
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(n):
-        ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / n
-    flops = 2.0 * 4.0 * S * S * (H * d) * B        # bwd = 2 x fwd, fwd = 4 S^2 dim per layer (SURVEY §8d)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+
+    ms = timeit(lambda: ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16))
+    ms_fwd = timeit(lambda: ops.attn_fwd(qkv, H, d, OCT_BF16))
+    flops = 2.0 * 4.0 * S * S * (H * d) * B
     achieved = flops / ms / 1e9
-    return {"kernel": "attn_bwd_tc_kernel<32> (+delta, dq-convert) decoder shape B8 S4097 H16 d32", "bound": "tensor",
+    n_exp = float(B) * H * S * S                       # one ex2 per score element per pass
+    sfu_peak = 16.0 * 148 * 1.965e9                    # MUFU: 16 ex2 / clk / SM at the max SM clock
+    # second data point: the biggest GEMM of the decoder block (fc1 + GELU epilogue), tensor-core bound
+    M, N, K = B * S, 2048, 512
+    a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.zeros(N, device=dev); o = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ms_gemm = timeit(lambda: ops.gemm(GEMM_NT, a, w, M, N, K, torch.bfloat16, EPI_BIAS, bias=bias, out=o, compute=OCT_BF16))
+    return {"kernel": "attn_bwd_tc_kernel<32> (+delta, dq-convert), decoder shape B8 S4097 H16 d32", "bound": "tensor",
             "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"],
-            "traffic": None, "ms_per_launch": ms, "peak_source": pk["src"],
-            "note": "algorithmic FLOPs (no recompute counted); inputs 100 MB qkv + 33 MB dout > L2 is not exceeded by much"}
+            "traffic": 306.0e6, "traffic_note": "dram read+write per launch from ncu --set full (profiles/r1_attention_ncu.md)",
+            "ms_per_launch": ms, "peak_source": pk["src"],
+            "sfu_bound": {"ex2_per_launch": n_exp, "achieved_gex2_s": n_exp / ms / 1e6, "peak_gex2_s": sfu_peak / 1e9,
+                          "frac": n_exp / (ms * 1e-3) / sfu_peak,
+                          "note": "head_dim 32: 128 MMA flop per score element, so ex2 throughput (16/clk/SM), not the tensor pipe, bounds this kernel"},
+            "attn_fwd": {"ms_per_launch": ms_fwd, "tflops": 4.0 * S * S * (H * d) * B / ms_fwd / 1e9,
+                         "sfu_frac": n_exp / (ms_fwd * 1e-3) / sfu_peak},
+            "gemm_fc1": {"shape": [M, N, K], "ms_per_launch": ms_gemm, "tflops": 2.0 * M * N * K / ms_gemm / 1e9,
+                         "frac_of_bf16_burst": 2.0 * M * N * K / ms_gemm / 1e9 / pk["bf16_burst"]},
+            "note": "algorithmic FLOPs (no recompute counted); inputs (100 MB qkv + 34 MB dout + 34 MB out) exceed the 126 MB L2"}
 
 
 if __name__ == "__main__":

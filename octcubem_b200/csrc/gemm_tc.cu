@@ -67,12 +67,12 @@ constexpr int kEpiStageBytes = 128 * 128;  // one [128 rows x 128 B] output grou
 
 template <int BLOCK_N>
 struct Cfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = (BLOCK_N == 256) ? 3 : 5;  // 144 / 160 KB of operands + 64 KB of output staging
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
-  uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // 2 x 16 KB, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 2 * kEpiStageBytes);
+  uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // 2 column halves x 2 buffers x 16 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 4 * kEpiStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -246,14 +246,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
     const int colhalf = (warp - 2) >> 2;
     const int tile_row = quarter * 32 + lane;
-    uint8_t* stg = smem_epi + colhalf * kEpiStageBytes;
-    uint8_t* stg_row = stg + tile_row * 128;
-    const uint32_t stg_addr = tc::smem_u32(stg);
+    uint8_t* stg_base = smem_epi + colhalf * 2 * kEpiStageBytes;  // two buffers, used alternately
+    int stg_sel = 0;
     const int bar_id = 1 + colhalf;
     const bool issuer = (quarter == 0) && (lane == 0);
     // 128-byte row segment (32 x 32-bit) -> staging tile -> TMA store of the [128 rows x 128 B] group at (col, row0)
     auto stage_and_store = [&](const uint32_t (&o)[32], const CUtensorMap* map, int col, int row0, bool reduce_add) {
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
+      uint8_t* stg = stg_base + stg_sel * kEpiStageBytes;
+      uint8_t* stg_row = stg + tile_row * 128;
+      const uint32_t stg_addr = tc::smem_u32(stg);
+      stg_sel ^= 1;
+      // the store issued two calls ago (same buffer) has left smem; the most recent one may still be in flight
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
       for (int q = 0; q < 8; ++q)
