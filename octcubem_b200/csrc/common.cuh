@@ -76,31 +76,33 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Fast GELU for the tensor-core epilogues.  erf via Abramowitz & Stegun 7.1.26 (|abs err| < 1.5e-7, two orders of
-// magnitude below bf16 rounding) with approximate SFU reciprocal / exp: 2 SFU ops + ~12 FMA-pipe ops instead of erff's
-// ~40 instructions.  The derivative shares the single exponential: exp(-(x/sqrt2)^2) == exp(-x^2/2).
-// The fp32 parity path keeps erff (gelu_erf / gelu_erf_grad).
-__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& e) {
+// Fast GELU for the tensor-core epilogues.  erfc via Abramowitz & Stegun 7.1.26 (|abs err| < 1.5e-7, two orders of
+// magnitude below bf16 rounding) with approximate SFU reciprocal / exp.  Written for instruction count: the epilogue warps
+// of the GELU GEMMs are issue- and XU-pipe-bound (profiles/r1_gemm_ncu.md), so the 1/2 is folded into the coefficients,
+// the sign select is replaced by max(x,0) - |x|*tail, and the derivative shares the single exponential
+// (exp(-(x/sqrt2)^2) == exp(-x^2/2)).  The fp32 parity path keeps erff (gelu_erf / gelu_erf_grad).
+//   tail = Phi(-|x|) = 0.5*erfc(|x|/sqrt2),   e = exp(-x^2/2)
+__device__ __forceinline__ void gelu_fast_parts(float x, float& tail, float& e) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
   poly *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));  // exp(-x^2/2)
-  const float half_tail = 0.5f * poly * e;            // 0.5 * (1 - erf(|x|/sqrt2))
-  cdf = (x >= 0.f) ? (1.f - half_tail) : half_tail;   // Phi(x)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (x * -0.72134752044448170368f)));
+  tail = poly * e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, e;
-  gelu_fast_parts(x, cdf, e);
-  return x * cdf;
+  float tail, e;
+  gelu_fast_parts(x, tail, e);
+  return fmaf(-fabsf(x), tail, fmaxf(x, 0.f));  // x >= 0: x - x*tail = x*Phi(x);  x < 0: x*tail = x*Phi(x)
 }
 __device__ __forceinline__ float gelu_fast_grad(float x) {
-  float cdf, e;
-  gelu_fast_parts(x, cdf, e);
+  float tail, e;
+  gelu_fast_parts(x, tail, e);
+  const float cdf = (x >= 0.f) ? (1.f - tail) : tail;
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 

@@ -42,6 +42,16 @@ int oct_make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void
   CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // A thread that has not touched the CUDA runtime yet (e.g. a fresh autograd worker): bind the context of the device
+    // that owns the operand, then retry.  Kernel launches do this implicitly, the driver-level encode call does not.
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, base) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+        cudaSetDevice(at.device) == cudaSuccess && cudaFree(nullptr) == cudaSuccess)
+      r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    (void)cudaGetLastError();
+  }
   if (r != CUDA_SUCCESS) {
     oct_set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d; base %p dims %llu,%llu stride %llu box %u,%u)", who,
                   (int)r, base, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
@@ -112,7 +122,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_full = tmem_empty + 2;  // [column half][buffer]: dGELU pre-activation tiles landed in the staging buffers
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = kPair ? (int)tc::cluster_ctarank() : 0;
@@ -137,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::mbar_init(&tmem_full[s], 1);
       tc::mbar_init(&tmem_empty[s], kEpiThreads);
     }
+    for (int s = 0; s < 4; ++s) tc::mbar_init(&aux_full[s], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_base_slot);
@@ -275,13 +287,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     };
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     for (int w = cta; w < num_work; w += ncta) {
       int m_blk, n_blk;
       tile_coords(w % num_tiles, m_blk, n_blk);
       const int row0 = m_blk * BLOCK_M;
-      const int row = row0 + tile_row;
       const int n0 = n_blk * BLOCK_N;
+      if (p.epilogue == OCT_EPI_DGELU && issuer) {
+        // dGELU: fetch this tile's pre-activations straight into the staging buffers (TMA, same swizzle as the store)
+        // while the MMAs of the tile are still running; the epilogue then works in place.  Per-lane global loads of
+        // 32 different rows per instruction cost as much as the per-lane stores did (profiles/r1_gemm_ncu.md).
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // earlier stores have drained both buffers
+        constexpr int kGroups = BLOCK_N / 128;
+#pragma unroll
+        for (int gg = 0; gg < kGroups; ++gg) {
+          const int nc = n0 + (colhalf * kGroups + gg) * 64;
+          if (nc < p.N) {
+            tc::mbar_arrive_expect_tx(&aux_full[colhalf * 2 + gg], kEpiStageBytes);
+            tc::tma_load_2d(stg_base + gg * kEpiStageBytes, &tmap_aux, &aux_full[colhalf * 2 + gg], nc, row0);
+          }
+        }
+      }
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
@@ -319,23 +345,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             stage_and_store(o, &tmap_aux, nc, row0, false);  // pre-activation
             // GELU is evaluated on the bf16-rounded pre-activation, like nn.GELU on a bf16 tensor
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = gelu_fast(bf16_round(v[i]));
-          } else if (p.epilogue == OCT_EPI_DGELU) {
-            if (row < p.M) {
-              const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + nc;
-#pragma unroll
-              for (int i = 0; i < 64; i += 8) {
-                if (nc + i < p.N) {
-                  const uint4 pre = *reinterpret_cast<const uint4*>(ax + i);
-                  const float2 a0 = unpack_bf16x2(pre.x), a1 = unpack_bf16x2(pre.y), a2 = unpack_bf16x2(pre.z),
-                               a3 = unpack_bf16x2(pre.w);
-                  v[i] *= gelu_fast_grad(a0.x); v[i + 1] *= gelu_fast_grad(a0.y);
-                  v[i + 2] *= gelu_fast_grad(a1.x); v[i + 3] *= gelu_fast_grad(a1.y);
-                  v[i + 4] *= gelu_fast_grad(a2.x); v[i + 5] *= gelu_fast_grad(a2.y);
-                  v[i + 6] *= gelu_fast_grad(a3.x); v[i + 7] *= gelu_fast_grad(a3.y);
-                }
-              }
+            for (int i = 0; i < 32; ++i) {
+              const float2 pre = unpack_bf16x2(o[i]);
+              v[2 * i] = gelu_fast(pre.x);
+              v[2 * i + 1] = gelu_fast(pre.y);
             }
+          } else if (p.epilogue == OCT_EPI_DGELU) {
+            uint8_t* stg = stg_base + gg * kEpiStageBytes;
+            uint8_t* stg_row = stg + tile_row * 128;
+            tc::mbar_wait(&aux_full[colhalf * 2 + gg], (aux_phase >> gg) & 1);
+            aux_phase ^= 1u << gg;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint4* slot = reinterpret_cast<uint4*>(stg_row + ((q ^ (tile_row & 7)) << 4));
+              const uint4 pre = *slot;
+              const float2 a0 = unpack_bf16x2(pre.x), a1 = unpack_bf16x2(pre.y), a2 = unpack_bf16x2(pre.z),
+                           a3 = unpack_bf16x2(pre.w);
+              const int i = 8 * q;
+              uint4 out;
+              out.x = pack_bf16x2(v[i] * gelu_fast_grad(a0.x), v[i + 1] * gelu_fast_grad(a0.y));
+              out.y = pack_bf16x2(v[i + 2] * gelu_fast_grad(a1.x), v[i + 3] * gelu_fast_grad(a1.y));
+              out.z = pack_bf16x2(v[i + 4] * gelu_fast_grad(a2.x), v[i + 5] * gelu_fast_grad(a2.y));
+              out.w = pack_bf16x2(v[i + 6] * gelu_fast_grad(a3.x), v[i + 7] * gelu_fast_grad(a3.y));
+              *slot = out;  // in place: each thread owns its 128-byte row segment
+            }
+            tc::fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (issuer && !(p.dbg & 1)) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmap_d)), "r"(tc::smem_u32(stg)), "r"(nc), "r"(row0) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -474,7 +515,7 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
     rc = oct_make_tmap(&td, dt, 2, D, dims, strides, box, "oct_gemm(bf16) D");
     if (rc) return rc;
     tx = td;
-    if (epilogue == OCT_EPI_BIAS_GELU) {
+    if (epilogue == OCT_EPI_BIAS_GELU || epilogue == OCT_EPI_DGELU) {
       rc = oct_make_tmap(&tx, dt, 2, aux, dims, strides, box, "oct_gemm(bf16) aux");
       if (rc) return rc;
     }

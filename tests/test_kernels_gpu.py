@@ -283,3 +283,23 @@ def test_patch_embed_tc(B, T, HW, E, u):
     want = O.patch_embed(imgs.double(), w.double(), b.double()).reshape(B, -1, E)
     out = ops.patch_embed_tc(imgs.to(DEV), w.view(E, -1).to(DEV).contiguous(), b.to(DEV), 16, u, torch.float32)
     assert rel(out, want) < 2e-3  # tf32 operands (10-bit mantissa), fp32 accumulate
+
+
+def test_gemm_tc_from_fresh_thread():
+    """A thread without a bound CUDA context (a new autograd worker) must be able to call the TMA-based GEMM."""
+    import threading
+    a = torch.randn(256, 128, device=DEV).bfloat16()
+    b = torch.randn(192, 128, device=DEV).bfloat16()
+    box = {}
+
+    def work():
+        try:
+            box["out"] = ops.gemm(GEMM_NT, a, b, 256, 192, 128, torch.float32, compute=OCT_BF16)
+        except Exception as e:  # noqa: BLE001
+            box["err"] = e
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert "err" not in box, box.get("err")
+    assert rel(box["out"], a.double() @ b.double().t()) < 2e-6
