@@ -4,10 +4,13 @@
 //
 // Forward: one CTA = 256 query rows (two 128-row tiles) of one (batch, head).  320 threads:
 //   warp 0     TMA producer: both Q tiles once, then K_j / V_j tiles through a ring (shared by the two Q tiles)
-//   warp 1     MMA issuer:   S_t = Q_t K_j^T (SS, K-major x K-major) into the TMEM S buffer of tile t;
-//              O_t += P_t V_j (TS: P read from TMEM as the A operand, V taken from the same row-major smem tile through
-//              an MN-major descriptor).  Issue order QK0, QK1, PV0, QK0', PV1, QK1', ... so that one tile's softmax
-//              always overlaps the other tile's MMAs.
+//   warp 1     MMA issuer:   S_t = Q_t K_j^T (SS, K-major x K-major) into one of THREE rotating TMEM score buffers
+//              (score tile n = 2j + t lives in buffer n % 3); O_t += P_t V_j (TS: P read from TMEM as the A operand, V
+//              taken from the same row-major smem tile through an MN-major descriptor).  Issue order
+//              QK(0) QK(1) QK(2) | PV(n) QK(n+3) ...: QK(n+3) reuses the buffer PV(n) has just consumed (the tensor
+//              pipe executes in issue order), so a warpgroup's next score tile is complete before it finishes the
+//              current one — with one buffer per Q tile the PV -> QK -> commit turnaround (~500 clk) sat on every
+//              warpgroup's critical path and the SFU idled 40 % of the time (profiles/r1_attention_ncu.md).
 //   warps 2-5  softmax warpgroup of Q tile 0, warps 6-9 of Q tile 1: thread <-> query row (TMEM lane), online softmax in
 //              the log2 domain with lazy rescaling (O is only rescaled when the running max grows by more than 2^8),
 //              P written back over S as bf16.
@@ -17,7 +20,7 @@
 
 namespace {
 
-constexpr int AT_BM = 128, AT_BN = 128, AT_QT = 2, AT_THREADS = 64 + AT_QT * 128, AT_KV_STAGES = 3;
+constexpr int AT_BM = 128, AT_BN = 128, AT_QT = 2, AT_THREADS = 64 + AT_QT * 128, AT_KV_STAGES = 4, AT_SBUFS = 3;
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -28,8 +31,8 @@ struct AtCfg {
   static constexpr uint32_t kSwz = (HD == 64) ? tc::kSwz128 : tc::kSwz64;
   static constexpr uint32_t kSBO = 8 * kRowBytes;                // 8-row swizzle atom
   static constexpr int kSmem = kTileBytes * (AT_QT + 2 * AT_KV_STAGES) + 1024 + 256;
-  static constexpr uint32_t kColS = 0;      // S_t at kColS + 128 t
-  static constexpr uint32_t kColO = 256;    // O_t at kColO + HD t
+  static constexpr uint32_t kColS = 0;                  // score tile n = 2j + t at kColS + 128 (n % AT_SBUFS)
+  static constexpr uint32_t kColO = 128 * AT_SBUFS;     // O_t at kColO + HD t  (384 + 2 HD <= 512)
 };
 
 struct AtParams {
@@ -126,9 +129,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + AT_KV_STAGES;
-  uint64_t* s_full = kv_empty + AT_KV_STAGES;  // [AT_QT]
-  uint64_t* p_full = s_full + AT_QT;           // [AT_QT]
-  uint64_t* o_done = p_full + AT_QT;           // [AT_QT]
+  // s_full / p_full are per score BUFFER (tile n and n + 3): QK(n+3) is issued behind PV(n), which waits for p_full(n),
+  // which the warpgroup arrives on after consuming s_full(n) — no barrier can run two phases ahead of its waiter
+  uint64_t* s_full = kv_empty + AT_KV_STAGES;  // [AT_SBUFS]
+  uint64_t* p_full = s_full + AT_SBUFS;        // [AT_SBUFS]
+  uint64_t* o_done = p_full + AT_SBUFS;        // [AT_QT]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + AT_QT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,11 +144,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     tc::prefetch_tmap(&tmap_qkv);
     tc::mbar_init(q_full, 1);
     for (int s = 0; s < AT_KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
-    for (int t = 0; t < AT_QT; ++t) {
-      tc::mbar_init(&s_full[t], 1);
-      tc::mbar_init(&p_full[t], 128);
-      tc::mbar_init(&o_done[t], 1);
+    for (int i = 0; i < AT_SBUFS; ++i) {
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_full[i], 128);
     }
+    for (int t = 0; t < AT_QT; ++t) tc::mbar_init(&o_done[t], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
@@ -172,53 +177,51 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     if (lane == 0) {
       constexpr uint32_t idesc_qk = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, AT_BN);
       constexpr uint32_t idesc_pv = tc::make_idesc(tc::kFmtBF16, false, true, AT_BM, HD);
-      auto issue_qk = [&](int t, int stage) {
+      auto issue_qk = [&](int n) {  // score tile n: Q tile n & 1 against K_(n >> 1)
+        const int t = n & 1, stage = (n >> 1) % AT_KV_STAGES;
         const uint32_t q_addr = tc::smem_u32(sQ + t * C::kTileBytes);
         const uint32_t k_addr = tc::smem_u32(sK + stage * C::kTileBytes);
+        const uint32_t d_addr = tmem_base + C::kColS + (n % AT_SBUFS) * 128;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint64_t da = tc::make_smem_desc(q_addr + k * 32, 16, C::kSBO, C::kSwz);
           const uint64_t db = tc::make_smem_desc(k_addr + k * 32, 16, C::kSBO, C::kSwz);
-          tc::mma_ss(tmem_base + C::kColS + t * 128, da, db, idesc_qk, k != 0);
+          tc::mma_ss(d_addr, da, db, idesc_qk, k != 0);
         }
-        tc::mma_commit(&s_full[t]);
+        tc::mma_commit(&s_full[n % AT_SBUFS]);
       };
-      auto issue_pv = [&](int t, int j, int stage) {
+      auto issue_pv = [&](int n) {
+        const int t = n & 1, j = n >> 1, stage = j % AT_KV_STAGES;
         const uint32_t v_addr = tc::smem_u32(sV + stage * C::kTileBytes);
+        const uint32_t p_addr = tmem_base + C::kColS + (n % AT_SBUFS) * 128;
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k) {
           // V as an MN-major B operand: 16 kv rows per step; one MN chunk (= HD elements) so LBO is unused
           const uint64_t db = tc::make_smem_desc(v_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
-          tc::mma_ts(tmem_base + C::kColO + t * HD, tmem_base + C::kColS + t * 128 + k * 8, db, idesc_pv, (j | k) != 0);
+          tc::mma_ts(tmem_base + C::kColO + t * HD, p_addr + k * 8, db, idesc_pv, (j | k) != 0);
         }
         tc::mma_commit(&o_done[t]);
       };
+      auto wait_kv = [&](int j) {
+        tc::mbar_wait(&kv_full[j % AT_KV_STAGES], (j / AT_KV_STAGES) & 1);
+        tc::tcgen05_fence_after();
+      };
+      const int n_tiles = 2 * n_kv;
       tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(&kv_full[0], 0);
-      tc::tcgen05_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      int stage = 0;                          // ring position of tile j
-      int nstage = 1 % AT_KV_STAGES; uint32_t nphase = (AT_KV_STAGES == 1) ? 1 : 0;  // ring position of tile j+1
-      for (int j = 0; j < n_kv; ++j) {
-        const bool more = (j + 1) < n_kv;
-        tc::mbar_wait(&p_full[0], j & 1);    // P_0(j) in TMEM (and O_0 rescaled if needed)
+      wait_kv(0);
+      issue_qk(0);
+      issue_qk(1);
+      if (n_kv > 1) { wait_kv(1); issue_qk(2); }
+      for (int n = 0; n < n_tiles; ++n) {
+        const int t = n & 1, j = n >> 1;
+        tc::mbar_wait(&p_full[n % AT_SBUFS], (n / AT_SBUFS) & 1);  // P(n) in TMEM (and O_t rescaled if needed)
         tc::tcgen05_fence_after();
-        issue_pv(0, j, stage);
-        if (more) {
-          tc::mbar_wait(&kv_full[nstage], nphase);
-          tc::tcgen05_fence_after();
-          issue_qk(0, nstage);                // overlaps softmax of tile 1
+        issue_pv(n);
+        if (t == 1) tc::mma_commit(&kv_empty[j % AT_KV_STAGES]);  // K_j, V_j fully consumed
+        if (n + AT_SBUFS < n_tiles) {
+          if (((n + AT_SBUFS) & 1) == 0) wait_kv((n + AT_SBUFS) >> 1);
+          issue_qk(n + AT_SBUFS);  // into the buffer PV(n) reads: ordered behind it on the tensor pipe
         }
-        tc::mbar_wait(&p_full[1], j & 1);
-        tc::tcgen05_fence_after();
-        issue_pv(1, j, stage);
-        tc::mma_commit(&kv_empty[stage]);     // K_j, V_j fully consumed
-        if (more) {
-          issue_qk(1, nstage);                // overlaps softmax of tile 0
-          if (++nstage == AT_KV_STAGES) { nstage = 0; nphase ^= 1; }
-        }
-        if (++stage == AT_KV_STAGES) stage = 0;
       }
     }
     __syncwarp();
@@ -228,20 +231,21 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t tmem_s = lane_addr + C::kColS + t * 128;
     const uint32_t tmem_o = lane_addr + C::kColO + t * HD;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      tc::mbar_wait(&s_full[t], j & 1);
+      const int n = 2 * j + t, buf = n % AT_SBUFS;
+      tc::mbar_wait(&s_full[buf], (n / AT_SBUFS) & 1);
       tc::tcgen05_fence_after();
       const int valid = p.S - j * AT_BN;  // columns >= valid are out of range (TMA zero-filled K rows)
+      const uint32_t tmem_s = lane_addr + C::kColS + buf * 128;
       if (valid >= AT_BN)
         softmax_tile<HD, false>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       else
         softmax_tile<HD, true>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&p_full[t]);
+      tc::mbar_arrive(&p_full[buf]);
     }
     // epilogue: O / l -> bf16, lse
     tc::mbar_wait(&o_done[t], (n_kv - 1) & 1);

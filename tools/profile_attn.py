@@ -18,3 +18,16 @@ for _ in range(3):
     dq = ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16)
 torch.cuda.synchronize()
 print("done", float(dq.float().abs().mean()))
+if len(sys.argv) > 2 and sys.argv[2] == "time":
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    print(f"[TIME] attn fwd {which}: {timeit(lambda: ops.attn_fwd(qkv, H, d, OCT_BF16)) * 1e3:.1f} us")
+    print(f"[TIME] attn bwd {which}: {timeit(lambda: ops.attn_bwd(qkv, out, dout, lse, H, d, OCT_BF16)) * 1e3:.1f} us")
