@@ -95,24 +95,37 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
     }
     m = m_new;
   }
-  // P = exp2(s * c - m) as bf16 pairs written over S (masked columns hold -inf -> exactly 0)
-  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  // P = exp2(s * c - m) as bf16 pairs written over S (masked columns hold -inf -> exactly 0).  Packed fp32x2 math
+  // (FFMA2 / FADD2) halves the issue slots around the exponentials, and one pair in kPolyEvery is evaluated by
+  // exp2_poly2 on the FMA pipe: the loop is bound by MUFU.EX2 (16 / clk / SM), so moving a quarter of the exponentials
+  // off the SFU shortens it (same idea as FlashAttention-4's software exp2).  The masked tile keeps the SFU for all
+  // columns so that -inf stays exactly 0.
+  constexpr int kPolyEvery = 4;
+  const uint64_t sc2 = tc::pack2(scale_log2e, scale_log2e), nm2 = tc::pack2(-m, -m);
+  uint64_t la = tc::pack2(0.f, 0.f), lb = la;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float p0 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i]), scale_log2e, -m));
-      const float p1 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i + 1]), scale_log2e, -m));
-      const float p2 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i + 2]), scale_log2e, -m));
-      const float p3 = tc::fast_exp2(fmaf(__uint_as_float(sr[c][2 * i + 3]), scale_log2e, -m));
-      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+    for (int i = 0; i < 16; ++i) {
+      const uint64_t x = tc::fma2(tc::pack2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])), sc2, nm2);
+      float p0, p1;
+      if (!kMasked && (i % kPolyEvery) == kPolyEvery - 1) {
+        tc::exp2_poly2(x, p0, p1);
+      } else {
+        float x0, x1;
+        tc::unpack2(x, x0, x1);
+        p0 = tc::fast_exp2(x0);
+        p1 = tc::fast_exp2(x1);
+      }
+      if (i & 1) lb = tc::add2(lb, tc::pack2(p0, p1)); else la = tc::add2(la, tc::pack2(p0, p1));
       pk[i] = pack_bf16x2(p0, p1);
-      pk[i + 1] = pack_bf16x2(p2, p3);
     }
     tc::tmem_st_x16(tmem_s + c * 16, pk);
   }
-  l += (l0 + l1) + (l2 + l3);
+  float l0, l1;
+  tc::unpack2(tc::add2(la, lb), l0, l1);
+  l += l0 + l1;
 }
 
 template <int HD>
@@ -174,7 +187,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop and the waits; the MMAs are issued under elect.sync.  Inside a `lane == 0` branch
+    // ptxas wraps EVERY tcgen05 instruction in an ELECT / BRA.U.ANY serialisation loop (it cannot prove a single active
+    // thread), which made this warp — not the SFU — the bottleneck of the kernel (93 % busy, profiles/r1_attention_ncu.md).
+    {
       constexpr uint32_t idesc_qk = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, AT_BN);
       constexpr uint32_t idesc_pv = tc::make_idesc(tc::kFmtBF16, false, true, AT_BM, HD);
       auto issue_qk = [&](int n) {  // score tile n: Q tile n & 1 against K_(n >> 1)
@@ -209,19 +225,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       const int n_tiles = 2 * n_kv;
       tc::mbar_wait(q_full, 0);
       wait_kv(0);
-      issue_qk(0);
-      issue_qk(1);
-      if (n_kv > 1) { wait_kv(1); issue_qk(2); }
+      if (n_kv > 1) wait_kv(1);
+      if (tc::elect_one()) {
+        issue_qk(0);
+        issue_qk(1);
+        if (n_kv > 1) issue_qk(2);
+      }
+      __syncwarp();
       for (int n = 0; n < n_tiles; ++n) {
         const int t = n & 1, j = n >> 1;
         tc::mbar_wait(&p_full[n % AT_SBUFS], (n / AT_SBUFS) & 1);  // P(n) in TMEM (and O_t rescaled if needed)
         tc::tcgen05_fence_after();
-        issue_pv(n);
-        if (t == 1) tc::mma_commit(&kv_empty[j % AT_KV_STAGES]);  // K_j, V_j fully consumed
-        if (n + AT_SBUFS < n_tiles) {
-          if (((n + AT_SBUFS) & 1) == 0) wait_kv((n + AT_SBUFS) >> 1);
-          issue_qk(n + AT_SBUFS);  // into the buffer PV(n) reads: ordered behind it on the tensor pipe
+        const bool more = n + AT_SBUFS < n_tiles;
+        if (more && ((n + AT_SBUFS) & 1) == 0) wait_kv((n + AT_SBUFS) >> 1);
+        if (tc::elect_one()) {
+          issue_pv(n);
+          if (t == 1) tc::mma_commit(&kv_empty[j % AT_KV_STAGES]);  // K_j, V_j fully consumed
+          if (more) issue_qk(n + AT_SBUFS);  // into the buffer PV(n) reads: ordered behind it on the tensor pipe
         }
+        __syncwarp();
       }
     }
     __syncwarp();

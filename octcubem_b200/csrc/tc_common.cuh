@@ -71,6 +71,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Latency-critical hand-offs (MMA issuer <-> softmax warps): poll with test_wait instead of suspending.  A suspended
+// try_wait is woken with a coarse granularity (the attention softmax warps spent 30 % of their time asleep behind
+// barriers that had already completed, profiles/r1_attention_ncu.md); polling costs two issue slots per ~30 clk.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 28)) {
+      printf("octcube_b200: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -228,6 +250,50 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100): one issue slot for two lanes' worth of work ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair on the FMA/ALU pipes instead of the SFU (the attention kernels are MUFU.EX2-bound at head_dim 32):
+// x = n + f with n = round(x) (magic-number add), 2^f by a degree-3 minimax polynomial on [-0.5, 0.5] (max rel. error
+// 7.6e-5, 50x below the bf16 rounding P receives), then n is added into the exponent field.  x is clamped to >= -126.
+__device__ __forceinline__ void exp2_poly2(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = add2(xc, pack2(12582912.f, 12582912.f));                      // low mantissa bits = round(x)
+  const uint64_t r = add2(t, pack2(-12582912.f, -12582912.f));                     // round(x) as a float
+  const uint64_t fr = fma2(r, pack2(-1.f, -1.f), xc);                              // x - round(x)
+  uint64_t p = fma2(pack2(0.05520550534129143f, 0.05520550534129143f), fr, pack2(0.24261397123336792f, 0.24261397123336792f));
+  p = fma2(p, fr, pack2(0.6932547688484192f, 0.6932547688484192f));
+  p = fma2(p, fr, pack2(0.9999276995658875f, 0.9999276995658875f));
+  float pa, pb, ta, tb;
+  unpack2(p, pa, pb);
+  unpack2(t, ta, tb);
+  p0 = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+  p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----
