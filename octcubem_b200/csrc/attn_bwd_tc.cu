@@ -134,7 +134,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop and the barrier waits; MMAs / commits are issued under elect.sync.  Inside a
+    // `lane == 0` branch ptxas wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop (attn_tc.cu has the numbers).
+    {
       constexpr uint32_t idesc_st = tc::make_idesc(tc::kFmtBF16, false, false, 128, AB_SUB);  // K Q_h^T, V dO_h^T
       constexpr uint32_t idesc_acc = tc::make_idesc(tc::kFmtBF16, false, true, 128, HD);       // P^T dO_h, dS^T Q_h (TS)
       constexpr uint32_t idesc_dq = tc::make_idesc(tc::kFmtBF16, true, true, 128, HD);         // dS K (A MN-major)
@@ -152,12 +154,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       constexpr uint32_t kKStepK = 32 >> 4, kKStepMN = (16 * C::kRowBytes) >> 4, kKStepDS = (16 * 128) >> 4;
       constexpr uint32_t kDsBufStep = C::kDsBytes >> 4;
       // sub-tile j -> (q tile j>>1, half j&1); its Q/dO ring stage is (j>>1) % AB_Q_STAGES, its fp32 stage is j&1
-      auto issue_sdp = [&](int j) {  // S^T = K Q_h^T ; dP^T = V dO_h^T into fp32 stage j&1
-        const int qstage = (j >> 1) % AB_Q_STAGES;
-        if ((j & 1) == 0) {  // first use of this Q/dO tile
-          tc::mbar_wait(&q_full[qstage], ((j >> 1) / AB_Q_STAGES) & 1);
+      auto wait_q = [&](int j) {  // all lanes: first use of Q/dO tile j >> 1
+        if ((j & 1) == 0) {
+          tc::mbar_wait(&q_full[(j >> 1) % AB_Q_STAGES], ((j >> 1) / AB_Q_STAGES) & 1);
           tc::tcgen05_fence_after();
         }
+      };
+      auto issue_sdp = [&](int j) {  // elected lane: S^T = K Q_h^T ; dP^T = V dO_h^T into fp32 stage j&1
+        const int qstage = (j >> 1) % AB_Q_STAGES;
         const uint32_t off = qstage * kStageStep + (j & 1) * kHalfStep;
         const uint32_t tcol = tmem_base + (j & 1) * C::kStageCols;
 #pragma unroll
@@ -169,8 +173,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         tc::mma_commit(&sdp_full[j & 1]);
       };
       tc::mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      if (n_sub > 1) issue_sdp(1);
+      wait_q(0);
+      if (tc::elect_one()) {
+        issue_sdp(0);
+        if (n_sub > 1) issue_sdp(1);
+      }
+      __syncwarp();
       for (int i = 0; i < n_sub; ++i) {
         const int m = i >> 1, hh = i & 1, st = i & 1;
         const int qstage = m % AB_Q_STAGES;
@@ -180,6 +188,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         tc::mbar_wait(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
         tc::tcgen05_fence_after();
         AB_TRACE(1);
+        if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < AB_SUB / 16; ++k)  // dV += P^T dO_h
           tc::mma_ts(tmem_base + C::kColDV, tcol + C::kColST + C::slice_off(k), dDO0_mn + off + k * kKStepMN, idesc_acc,
@@ -188,24 +197,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         for (int k = 0; k < AB_SUB / 16; ++k)  // dK += dS^T Q_h
           tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
                      (i | k) != 0);
+        if (hh == 1) tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves issued earlier)
+        }
+        __syncwarp();
         if (hh == 1) {
-          tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves was issued earlier)
           if (m > 0) {
             tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM
             tc::tcgen05_fence_after();
           }
-          const uint32_t dsoff = (m & 1) * kDsBufStep;
+          if (tc::elect_one()) {
+            const uint32_t dsoff = (m & 1) * kDsBufStep;
 #pragma unroll
-          for (int k = 0; k < 128 / 16; ++k)  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
-            tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + dsoff + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
-          tc::mma_commit(dq_full);
+            for (int k = 0; k < 128 / 16; ++k)  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
+              tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + dsoff + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
+            tc::mma_commit(dq_full);
+          }
+          __syncwarp();
         }
         AB_TRACE(2);
         // scores of sub-tile i+2 reuse fp32 stage st: queued behind the MMAs above, which read its bf16 contents
-        if (i + 2 < n_sub) issue_sdp(i + 2);
+        if (i + 2 < n_sub) {
+          wait_q(i + 2);
+          if (tc::elect_one()) issue_sdp(i + 2);
+          __syncwarp();
+        }
         AB_TRACE(3);
       }
-      tc::mma_commit(acc_full);
+      if (tc::elect_one()) tc::mma_commit(acc_full);
     }
     __syncwarp();
   } else {
