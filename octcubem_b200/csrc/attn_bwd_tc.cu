@@ -40,7 +40,7 @@ struct AbCfg {
   static constexpr int kDsBytes = 2 * 128 * 128;  // one dS^T staging tile: two 64-query chunks of [128 kv rows x 128 B]
   static constexpr int kDqBytes = 128 * HD * 4;   // fp32 dQ tile staged for the bulk reduce (16-byte chunks XOR-swizzled)
   // smem: K, V | Q[2], dO[2] | dS[2] | dQ staging | lse2[2][128], delta[2][128] | barriers
-  static constexpr int kSmem = 2 * kTileBytes + 2 * AB_Q_STAGES * kTileBytes + 2 * kDsBytes + kDqBytes + 4 * 128 * 4 + 1024 + 256;
+  static constexpr int kSmem = 2 * kTileBytes + 2 * AB_Q_STAGES * kTileBytes + 2 * kDsBytes + kDqBytes + 8 * 2 * 64 * 4 + 1024 + 256;
   // TMEM columns: stage s of the fp32 sub-tiles: S^T at 128 s, dP^T at 128 s + 64; accumulators behind them
   static constexpr uint32_t kColST = 0, kColDPT = 64, kStageCols = 128;
   static constexpr uint32_t kColDV = 256, kColDK = 256 + HD, kColDQ = 256 + 2 * HD;
@@ -82,9 +82,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint8_t* sDO = sQ + AB_Q_STAGES * C::kTileBytes;        // [AB_Q_STAGES]
   uint8_t* sDS = sDO + AB_Q_STAGES * C::kTileBytes;       // [2] x 32 KB, 1024-aligned (all tiles are multiples of 8 KB)
   uint8_t* sDQ = sDS + 2 * C::kDsBytes;                   // [128][HD] fp32, swizzled
-  float* sLse = reinterpret_cast<float*>(sDQ + C::kDqBytes);  // [2][128]
-  float* sDelta = sLse + 2 * 128;                             // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * 128);
+  float* sStat = reinterpret_cast<float*>(sDQ + C::kDqBytes);  // [8 warps][2 slots][32 x -lse*log2e | 32 x -delta]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 8 * 2 * 64);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;                 // [2]
   uint64_t* q_empty = q_full + AB_Q_STAGES;    // [2]
@@ -235,16 +234,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const bool partial_kv = (n0 + AB_T) > p.S;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const size_t bh = (size_t)b * p.H + h;
-    // per-query statistics of a q tile, fetched one tile ahead (raw values; transformed when stored):
-    // threads 0..127 own lse, 128..255 own delta
-    auto ld_stat = [&](int m) {
-      const int qi = min(m * AB_T + (tid & 127), p.S - 1);
-      return (tid < 128) ? p.lse[bh * p.S + qi] : p.delta[bh * p.S + qi];
+    // The eight warps never synchronise with each other (only through p_ready -> the MMA issuer): each warp stages the
+    // statistics of ITS 32 query columns and drains ITS 32 x HD/2 block of dQ.  CTA-wide bar.syncs here cost ~900 clk
+    // per query tile in warp skew (clock64 trace, profiles/r1_attention_ncu.md).
+    // per-query statistics of this warp's columns of a sub-tile, fetched one sub-tile ahead (raw; transformed when stored)
+    auto stat_q = [&](int i) { return (i >> 1) * AB_T + (i & 1) * AB_SUB + colhalf * 32 + lane; };
+    auto ld_stat = [&](int i, float& a, float& d) {
+      const size_t idx = bh * p.S + min(stat_q(i), p.S - 1);
+      a = p.lse[idx];
+      d = p.delta[idx];
     };
-    // TMEM -> registers -> swizzled smem tile -> ONE asynchronous bulk reduction into the fp32 accumulator
-    auto drain_dq = [&](int m) {
+    // TMEM -> registers -> per-warp smem block -> ONE asynchronous bulk reduction of that block into the fp32 accumulator.
+    // Accumulator layout per 128-query tile: [warp][16-byte chunk][32 rows][4 floats] (attn_dq_convert_kernel undoes it):
+    // contiguous per warp, and the st.shared.v4 of a warp hit 32 different bank groups.
+    constexpr int kWarpDqBytes = HD * 64;  // 32 rows x HD/2 columns fp32
+    uint8_t* sdq_w = sDQ + warp * kWarpDqBytes;
+    auto drain_dq = [&](int m, int i) {
       tc::mbar_wait(dq_full, m & 1);
       tc::tcgen05_fence_after();
+      AB_TRACE(10);
       uint32_t o[HD / 2];
       if (HD == 32) {
         uint32_t(&o16)[16] = reinterpret_cast<uint32_t(&)[16]>(o);
@@ -256,36 +264,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tc::tmem_ld_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(dq_free);  // dQ columns are in registers: the issuer may overwrite the TMEM tile
-      // the bulk reduction issued one query tile ago must have finished reading the staging buffer
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      uint8_t* srow = sDQ + row * (HD * 4);
+      AB_TRACE(11);
+      // this warp's bulk reduction of the previous query tile must have finished reading its staging block
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      AB_TRACE(12);
 #pragma unroll
-      for (int q = 0; q < HD / 8; ++q) {  // 16-byte chunk j of this row lands at chunk (j & 8) | ((j ^ row) & 7)
-        const int j = colhalf * (HD / 8) + q;
-        const int pos = (j & 8) | ((j ^ row) & 7);
-        *reinterpret_cast<uint4*>(srow + pos * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-      }
+      for (int q = 0; q < HD / 8; ++q)
+        *reinterpret_cast<uint4*>(sdq_w + (q * 32 + lane) * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       tc::fence_proxy_async();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (tid == 0) {
-        float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD;
+      __syncwarp();
+      AB_TRACE(13);
+      if (lane == 0) {
+        float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD + warp * (kWarpDqBytes / 4);
         asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                     "r"(tc::smem_u32(sDQ)), "r"((uint32_t)C::kDqBytes)
+                     "r"(tc::smem_u32(sdq_w)), "r"((uint32_t)kWarpDqBytes)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
-    float stat = ld_stat(0);
+    float raw_lse, raw_delta;
+    ld_stat(0, raw_lse, raw_delta);
     for (int i = 0; i < n_sub; ++i) {
       const int m = i >> 1, hh = i & 1, st = i & 1;
-      const int slot = m & 1;
-      if (hh == 0) {
-        const bool ok = (m * AB_T + (tid & 127)) < p.S;
-        if (tid < 128) sLse[slot * 128 + tid] = ok ? stat * kLog2e : INFINITY;
-        else sDelta[slot * 128 + (tid & 127)] = ok ? stat : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (m + 1 < n_q) stat = ld_stat(m + 1);
+      float* stat = sStat + warp * 128 + (i & 1) * 64;  // slot last read two sub-tiles ago by this same warp
+      {
+        const bool ok = stat_q(i) < p.S;
+        stat[lane] = ok ? -raw_lse * kLog2e : -INFINITY;  // negated, log2 domain: x = s * scale + stat
+        stat[32 + lane] = ok ? -raw_delta : 0.f;          // negated: dP + (-delta) is one FADD2
+        __syncwarp();
+        if (i + 1 < n_sub) ld_stat(i + 1, raw_lse, raw_delta);
       }
       const uint32_t tcol = lane_addr + st * C::kStageCols + colhalf * 32;
       AB_TRACE(4);
@@ -298,21 +306,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tc::tmem_ld_wait();
       AB_TRACE(6);
       uint32_t pk[16], dk[16];
-      const float4* l4 = reinterpret_cast<const float4*>(sLse + slot * 128 + hh * AB_SUB + colhalf * 32);
-      const float4* d4 = reinterpret_cast<const float4*>(sDelta + slot * 128 + hh * AB_SUB + colhalf * 32);
+      const float4* l4 = reinterpret_cast<const float4*>(stat);
+      const float4* d4 = reinterpret_cast<const float4*>(stat + 32);
+      // Packed fp32x2 math (FFMA2 / FADD2 / FMUL2): half the issue slots around the exponentials.  No masking is
+      // needed: query columns past S carry lse = +inf (P = 0), and kv rows past S have zero-filled K / V rows, so
+      // their (finite) P and dS only reach dV / dK rows that are never stored and add dS * 0 to dQ.
+      const uint64_t sc2 = tc::pack2(p.scale_log2e, p.scale_log2e);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 lv = l4[q], dv = d4[q];
-        float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q]), p.scale_log2e, -lv.x));
-        float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q + 1]), p.scale_log2e, -lv.y));
-        float p2 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q + 2]), p.scale_log2e, -lv.z));
-        float p3 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * q + 3]), p.scale_log2e, -lv.w));
-        // rows past S exist only in the last kv tile (zero K rows would still give p = exp2(-lse) != 0)
-        if (partial_kv && !kv_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-        const float d0 = p0 * (__uint_as_float(dp[4 * q]) - dv.x);
-        const float d1 = p1 * (__uint_as_float(dp[4 * q + 1]) - dv.y);
-        const float d2 = p2 * (__uint_as_float(dp[4 * q + 2]) - dv.z);
-        const float d3 = p3 * (__uint_as_float(dp[4 * q + 3]) - dv.w);
+        const uint64_t xa = tc::fma2(tc::pack2(__uint_as_float(s[4 * q]), __uint_as_float(s[4 * q + 1])), sc2,
+                                     tc::pack2(lv.x, lv.y));
+        const uint64_t xb = tc::fma2(tc::pack2(__uint_as_float(s[4 * q + 2]), __uint_as_float(s[4 * q + 3])), sc2,
+                                     tc::pack2(lv.z, lv.w));
+        float x0, x1, x2, x3;
+        tc::unpack2(xa, x0, x1);
+        tc::unpack2(xb, x2, x3);
+        const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1), p2 = tc::fast_exp2(x2), p3 = tc::fast_exp2(x3);
+        const uint64_t da = tc::mul2(tc::pack2(p0, p1), tc::add2(tc::pack2(__uint_as_float(dp[4 * q]), __uint_as_float(dp[4 * q + 1])),
+                                                                 tc::pack2(dv.x, dv.y)));
+        const uint64_t db = tc::mul2(tc::pack2(p2, p3), tc::add2(tc::pack2(__uint_as_float(dp[4 * q + 2]), __uint_as_float(dp[4 * q + 3])),
+                                                                 tc::pack2(dv.z, dv.w)));
+        float d0, d1, d2, d3;
+        tc::unpack2(da, d0, d1);
+        tc::unpack2(db, d2, d3);
         pk[2 * q] = pack_bf16x2(p0, p1);
         pk[2 * q + 1] = pack_bf16x2(p2, p3);
         dk[2 * q] = pack_bf16x2(d0, d1);
@@ -334,15 +351,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&p_ready[st]);
       AB_TRACE(8);
-      // deferred drain: dQ of the previous query tile was queued a full sub-tile ago
-      if (hh == 0 && m > 0) drain_dq(m - 1);
+      // deferred drain: dQ of the previous query tile was queued TWO sub-tiles ago.  One sub-tile was not enough: its
+      // eight MN-major SS MMAs (~130 clk each) run behind dV/dK of the same iteration, and these warps — the critical
+      // path of the kernel — sat ~470 clk per query tile in the dq_full wait (clock64 trace, profiles/r1_attention_ncu.md).
+      // The issuer waits for dq_free right after this sub-tile's p_ready, so the drain costs it ~200 clk of its slack.
+      if (hh == 1 && m > 0) drain_dq(m - 1, i);
       AB_TRACE(9);
     }
-    drain_dq(n_q - 1);
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    drain_dq(n_q - 1, 0);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
       for (int i = 0; i < 8; ++i)
-        for (int k = 0; k < 10; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
+        for (int k = 0; k < 14; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
     }
     // epilogue: column half 0 stores dV, half 1 stores dK of this kv tile
     tc::mbar_wait(acc_full, 0);
@@ -413,9 +433,11 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bf
   const int hh = (int)(r % H); r /= H;
   const int s = (int)(r % S);
   const int64_t bb = r / S;
-  // the accumulator rows are stored with their 16-byte chunks XOR-swizzled (see the drain in attn_bwd_tc_kernel)
-  const int pos = (c4 & 8) | ((c4 ^ s) & 7);
-  const float4 v = *reinterpret_cast<const float4*>(dq_acc + ((bb * H + hh) * Spad + s) * HD + pos * 4);
+  // accumulator layout per 128-query tile: [warp = 4 * column half + row quarter][chunk][32 rows][4 floats]
+  // (see the per-warp drain in attn_bwd_tc_kernel)
+  const int rr = s & 127, wq = (c4 / (HD / 8)) * 4 + (rr >> 5), q = c4 % (HD / 8);
+  const float4 v = *reinterpret_cast<const float4*>(dq_acc + ((bb * H + hh) * Spad + (s & ~127)) * HD +
+                                                    ((wq * (HD / 8) + q) * 32 + (rr & 31)) * 4);
   __nv_bfloat16* dst = dqkv + (((bb * S + s) * 3 + 0) * H + hh) * HD + c4 * 4;
   Vec4<__nv_bfloat16>::st(dst, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
 }
