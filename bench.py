@@ -260,11 +260,30 @@ def main_b200(args):
     ms_step = ms_total / args.steps
     value = world * BATCH / (ms_step / 1e3)
 
-    # end to end through the public API: pinned host volume -> device, step, loss -> host, every step
+    # end to end through the public API: pinned host volume -> device, step, loss -> host, every step.  Like any training
+    # input pipeline (pin_memory + non_blocking prefetch) the upload of step i+1 runs on a copy stream while step i
+    # computes: H2D lands in a staging buffer, a device-side copy moves it into the graph's input at the top of the step.
+    copy_stream = torch.cuda.Stream()
+    stage = torch.empty_like(vol)
+    h2d_done, stage_free = torch.cuda.Event(), torch.cuda.Event()
+
+    def upload():
+        copy_stream.wait_event(stage_free)
+        with torch.cuda.stream(copy_stream):
+            stage.copy_(host_vol, non_blocking=True)
+            h2d_done.record(copy_stream)
+
+    stage_free.record()
+    upload()
+
     def e2e_step():
-        vol.copy_(host_vol, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(h2d_done)
+        vol.copy_(stage, non_blocking=True)
+        stage_free.record(cur)
+        upload()                      # next step's volumes: overlaps this step's compute
         run()
-        return loss_out.item()
+        return loss_out.item()        # device -> host read of the loss: the host observes every step's result
 
     for _ in range(3):
         e2e_step()
@@ -297,7 +316,8 @@ def main_b200(args):
                        "cuda_graph": graph is not None,
                        "l2": "per-step working set (1.3 GB fp32 weights + bf16 shadows + ~10 GB activations) >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "volumes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": host_vol.numel() * 4 * 1,
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4,
+                    "pipeline": "upload of step i+1 (pinned, copy stream, staging buffer) overlaps step i; one H2D per timed step"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,

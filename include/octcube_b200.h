@@ -111,6 +111,14 @@ int oct_gemm(int compute, int layout, const void* A, const void* B, void* D, int
              int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int epilogue, const float* bias, void* aux, int beta,
              oct_stream_t stream);
 
+/* ---- nn.Linear weight + bias gradient in ONE tensor-core kernel (replaces cuBLASLt wgrad + the sum-over-tokens reduction
+ * autograd runs for every Linear: FA:mha.py:635,703, FA:mlp.py:48-50, models:511,595) -------------------------------
+ * dw [n_out, ld_dw] f32 (= | +=) dy[tokens, n_out]^T x[tokens, k_in] ; db [n_out] f32 (= | +=) sum_t dy[t, :]
+ * dy, x bf16 row-major (ld_dy, ld_x elements per row).  The bias gradient is one extra 128x16x16 tcgen05.mma per k-step
+ * against a constant tile of ones (dy is already in shared memory as the A operand).  compute must be OCT_BF16. */
+int oct_gemm_wgrad_bias(int compute, const void* dy, const void* x, float* dw, float* db, int64_t n_out, int64_t k_in,
+                        int64_t tokens, int64_t ld_dy, int64_t ld_x, int64_t ld_dw, int beta, oct_stream_t stream);
+
 /* ---- self-attention on packed qkv (FA:mha.py:122-130 flash_attn_qkvpacked_func, non-causal, p=0) -----------
  * qkv [B,S,3,H,d] ; out [B,S,H,d] ; lse [B,H,S] f32 (natural-log-sum-exp of scaled scores) ; scale = d^-0.5.
  * compute = OCT_BF16: tcgen05 flash kernel (d in {32,64}); OCT_F32: fp32 CUDA-core kernel (d <= 128). */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "oct_add_ln_bwd_ws_bytes": (Z, [L, L]),
     "oct_add_ln_bwd": (I, [P, I, P, I, P, P, P, P, P, P, I, P, P, P, Z, L, L, P]),
     "oct_gemm": (I, [I, I, P, P, P, I, L, L, L, L, L, L, I, P, P, I, P]),
+    "oct_gemm_wgrad_bias": (I, [I, P, P, P, P, L, L, L, L, L, L, I, P]),
     "oct_attn_fwd": (I, [I, P, P, P, L, L, L, L, F, P]),
     "oct_attn_bwd_ws_bytes": (Z, [I, L, L, L, L]),
     "oct_attn_bwd": (I, [I, P, P, P, P, P, P, Z, L, L, L, L, F, P]),

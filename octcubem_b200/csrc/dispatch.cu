@@ -5,7 +5,7 @@ int oct_gemm_simt_f32(int layout, const float* A, const float* B, float* D, int6
                       int64_t ldb, int64_t ldd, int epilogue, const float* bias, float* aux, int beta, cudaStream_t stream);
 int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dtype, int64_t M, int64_t N, int64_t K,
                      int64_t lda, int64_t ldb, int64_t ldd, int epilogue, const float* bias, void* aux, int beta,
-                     cudaStream_t st);
+                     float* colsum, cudaStream_t st);
 int oct_attn_fwd_simt(int io_dtype, const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H, int64_t d,
                       float scale, cudaStream_t st);
 int oct_attn_bwd_simt(int io_dtype, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -33,10 +33,22 @@ extern "C" int oct_gemm(int compute, int layout, const void* A, const void* B, v
   }
   if (compute == OCT_BF16) {
     OCT_REQUIRE(d_dtype == OCT_F32 || d_dtype == OCT_BF16, "oct_gemm(bf16): bad D dtype");
-    return oct_gemm_tc_bf16(layout, A, B, D, d_dtype, M, N, K, lda, ldb, ldd, epilogue, bias, aux, beta,
+    return oct_gemm_tc_bf16(layout, A, B, D, d_dtype, M, N, K, lda, ldb, ldd, epilogue, bias, aux, beta, nullptr,
                             (cudaStream_t)stream);
   }
   OCT_REQUIRE(false, "oct_gemm: bad compute mode %d", compute);
+}
+
+extern "C" int oct_gemm_wgrad_bias(int compute, const void* dy, const void* x, float* dw, float* db, int64_t n_out,
+                                   int64_t k_in, int64_t tokens, int64_t ld_dy, int64_t ld_x, int64_t ld_dw, int beta,
+                                   oct_stream_t stream) {
+  OCT_REQUIRE(dy && x && dw && db, "oct_gemm_wgrad_bias: null pointer");
+  OCT_REQUIRE(n_out >= 0 && k_in >= 0 && tokens > 0, "oct_gemm_wgrad_bias: bad dimension");
+  OCT_REQUIRE(beta == 0 || beta == 1, "oct_gemm_wgrad_bias: beta must be 0 or 1");
+  OCT_REQUIRE(compute == OCT_BF16, "oct_gemm_wgrad_bias: only the bf16 tensor-core path fuses the bias gradient "
+                                   "(fp32 mode: oct_gemm + oct_colsum)");
+  return oct_gemm_tc_bf16(OCT_GEMM_TN, dy, x, dw, OCT_F32, n_out, k_in, tokens, ld_dy, ld_x, ld_dw, OCT_EPI_NONE, nullptr,
+                          nullptr, beta, db, (cudaStream_t)stream);
 }
 
 extern "C" int oct_attn_fwd(int compute, const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,

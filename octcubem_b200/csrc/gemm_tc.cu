@@ -75,14 +75,24 @@ constexpr int kGroupM = 8;    // tile rasterisation: groups of 8 m-blocks sweep 
 
 constexpr int kEpiStageBytes = 128 * 128;  // one [128 rows x 128 B] output group per column half
 
-template <int BLOCK_N>
+constexpr int kOnesBytes = 16 * 128;  // [16 rows x 64 bf16] tile of ones: B operand of the bias-gradient MMA (kColsum)
+
+// kColsum (wgrad + bias gradient in one kernel, TN layout only): next to D = A^T B the kernel accumulates
+// colsum[m] = sum_k A[k, m] = (A^T 1)[m] with one extra 128x16x16 MMA per k-step against a constant tile of ones, into 16
+// TMEM columns behind a SINGLE accumulator stage (2 x 256 + 16 columns do not fit the 512-column TMEM).  It replaces a
+// separate pass over dY per nn.Linear (131 column-sum launches, 5.5 % of the step, profiles/r1_step_launches.md);
+// wgrad-shaped problems map one work item to each CTA, so the second accumulator stage was idle there anyway.
+template <int BLOCK_N, bool kColsum>
 struct Cfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 3 : 5;  // 144 / 160 KB of operands + 64 KB of output staging
+  static constexpr int kStages = (BLOCK_N == 256) ? 3 : (kColsum ? 4 : 5);  // 144 / 160 KB of operands + 64 KB of output staging
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kAccStages = kColsum ? 1 : 2;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages, or one + the colsum columns (power of two: 256 or 512)
+  static constexpr int kColsumCol = BLOCK_N;     // TMEM column of the bias-gradient accumulator (kColsum)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + (kColsum ? kOnesBytes : 0) +
+                                    1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -97,6 +107,7 @@ struct GemmParams {
   int dbg;           // OCT_GEMM_DBG timing experiments (0 in production): 1 = epilogue skips its global stores
   int splits;        // split-K factor (fp32 D, EPI_NONE only): partial products are reduced with red.global.add
   int kb_per_split;  // k-blocks per split
+  float* colsum;     // kColsum: [M] fp32, (+)= column sums of the MN-major A operand (the bias gradient of a wgrad)
 };
 
 // kPair: the grid is launched in clusters of two CTAs that work on vertically adjacent 128-row tiles of the same
@@ -104,20 +115,22 @@ struct GemmParams {
 // L2 -> SM operand traffic per MMA drops from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2-bandwidth-bound at
 // ~26 TB/s demand, profiles/r1_gemm_ncu.md).  A stage may only be refilled once BOTH CTAs' MMAs have consumed it,
 // hence the multicast tcgen05.commit onto both empty barriers (arrival count 2).
-template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair>
+template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair, bool kColsum>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                               const __grid_constant__ CUtensorMap tmap_b,
                                                               const __grid_constant__ CUtensorMap tmap_d,
                                                               const __grid_constant__ CUtensorMap tmap_aux,
                                                               const GemmParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, kColsum>;
+  static_assert(!kColsum || A_MN, "the bias-gradient MMA sums the MN-major A operand over K");
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
   uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // 2 column halves x 2 buffers x 16 KB, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 4 * kEpiStageBytes);
+  uint8_t* smem_ones = smem_epi + 4 * kEpiStageBytes;      // kColsum: 2 KB of bf16 1.0, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + (kColsum ? kOnesBytes : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -152,6 +165,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  if (kColsum) {
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem_ones)[i] = 0x3F803F80u;
+    tc::fence_proxy_async();  // generic-proxy stores -> tcgen05.mma operand reads
+  }
   tc::tcgen05_fence_before();
   __syncthreads();
   if (kPair) tc::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
@@ -216,12 +233,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = tc::make_idesc(tc::kFmtBF16, A_MN, B_MN, BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc_cs = tc::make_idesc(tc::kFmtBF16, A_MN, false, BLOCK_M, 16);  // A^T x ones[16 x K] (K-major)
+    const uint64_t d_ones = tc::make_smem_desc(tc::smem_u32(smem_ones), 16, 1024);         // every k-slice is all ones
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = cta; w < num_work; w += ncta) {
       if (lane == 0) {
+        bool with_colsum = false;
+        if (kColsum) {  // the n-block-0 tile of every m-block row carries the column sums of its A tiles
+          int m_blk, n_blk;
+          tile_coords(w % num_tiles, m_blk, n_blk);
+          with_colsum = (n_blk == 0);
+        }
         tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -239,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint64_t db = B_MN ? tc::make_smem_desc(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : tc::make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
             tc::mma_ss(tmem_d, da, db, idesc, (kb | k) != 0);
+            if (kColsum && with_colsum) tc::mma_ss(tmem_base + C::kColsumCol, da, d_ones, idesc_cs, (kb | k) != 0);
           }
           // frees the smem slot once these MMAs have read it (in both CTAs of a pair: the peer multicasts into it)
           if (kPair) tc::mma_commit_mc(&empty_bar[stage], 3); else tc::mma_commit(&empty_bar[stage]);
@@ -247,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         tc::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -311,6 +337,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      if (kColsum && n_blk == 0 && colhalf == 0) {
+        // bias gradient of rows [row0, row0 + 128): all 16 columns of the ones-MMA hold the same sum; lane <-> row
+        const float cs = __uint_as_float(tc::tmem_ld_x1(tmem_base + ((uint32_t)(quarter * 32) << 16) + C::kColsumCol));
+        if (row0 + tile_row < p.M) {
+          if (p.beta != 0 || p.splits > 1) atomicAdd(p.colsum + row0 + tile_row, cs);
+          else p.colsum[row0 + tile_row] = cs;
+        }
+      }
       if (p.d_bf16) {
         constexpr int kGroups = BLOCK_N / 128;  // 64-column (128-byte) groups per column half
 #pragma unroll 1
@@ -417,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&tmem_empty[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have left smem and are visible
   }
@@ -431,11 +465,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
-template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair>
+template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair, bool kColsum = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx, const GemmParams& p,
            cudaStream_t st) {
-  using C = Cfg<BLOCK_N>;
-  auto kern = gemm_tc_kernel<A_MN, B_MN, BLOCK_N, kPair>;
+  using C = Cfg<BLOCK_N, kColsum>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, BLOCK_N, kPair, kColsum>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -484,7 +518,9 @@ int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t 
 
 int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dtype, int64_t M, int64_t N, int64_t K,
                      int64_t lda, int64_t ldb, int64_t ldd, int epilogue, const float* bias, void* aux, int beta,
-                     cudaStream_t st) {
+                     float* colsum, cudaStream_t st) {
+  OCT_REQUIRE(!colsum || (layout == OCT_GEMM_TN && d_dtype == OCT_F32 && epilogue == OCT_EPI_NONE),
+              "oct_gemm(bf16): the fused column sum needs the TN layout, fp32 D and no epilogue");
   OCT_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D), "oct_gemm(bf16): operands must be 16-byte aligned");
   OCT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "oct_gemm(bf16): lda/ldb must be multiples of 8 (TMA 16-byte strides)");
   OCT_REQUIRE(N % 8 == 0 && ldd % 8 == 0, "oct_gemm(bf16): N and ldd must be multiples of 8");
@@ -522,27 +558,44 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   }
   GemmParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.ldd = ldd; p.D = D; p.d_bf16 = (d_dtype == OCT_BF16);
-  p.epilogue = epilogue; p.bias = bias; p.aux = aux; p.beta = beta;
+  p.epilogue = epilogue; p.bias = bias; p.aux = aux; p.beta = beta; p.colsum = colsum;
   { const char* e = getenv("OCT_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   // split-K: wgrad-shaped problems (few output tiles, long contraction) would otherwise occupy a fraction of the chip
   p.splits = 1;
   const int num_kb = (int)ceil_div64(K, BLOCK_K);
   p.kb_per_split = num_kb;
-  if (d_dtype == OCT_F32 && epilogue == OCT_EPI_NONE) {
+  if (d_dtype == OCT_F32 && epilogue == OCT_EPI_NONE && num_kb >= 16) {
+    // Work items = tiles x splits are dealt round-robin to one CTA per SM: pick the split count that minimises
+    // rounds x (k-blocks per item + the item's epilogue, ~6 k-blocks' worth for a 128x256 fp32 reducing store), keeping
+    // >= 8 k-blocks (512 of K) per split.  E.g. the encoder Wqkv wgrad (96 tiles, 52 k-blocks) runs as 3 x 96 items in two
+    // rounds of 18 instead of one round of 52 on 96 of the 148 SMs.
     const int64_t tiles = ceil_div64(M, pair ? 2 * BLOCK_M : BLOCK_M) * ceil_div64(N, block_n) * (pair ? 2 : 1);
     const int sms = oct_num_sms();
-    if (tiles * 2 <= sms && num_kb >= 16) {
-      int splits = (int)(sms / tiles);
-      if (splits > num_kb / 8) splits = num_kb / 8;  // keep >= 8 k-blocks (512 of K) per split
-      if (splits > 1) {
-        p.kb_per_split = (num_kb + splits - 1) / splits;
-        p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-        if (!beta) {
-          cudaError_t e = cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st);
-          if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
-        }
+    const int kEpiCost = 6;
+    int best = 1;
+    int64_t best_cost = ceil_div64(tiles, sms) * (num_kb + kEpiCost);
+    for (int s = 2; s <= num_kb / 8 && s <= 64; ++s) {
+      const int per = (num_kb + s - 1) / s;
+      const int eff = (num_kb + per - 1) / per;
+      const int64_t cost = ceil_div64(tiles * eff, sms) * (per + kEpiCost);
+      if (cost < best_cost) { best_cost = cost; best = s; }
+    }
+    if (best > 1) {
+      p.kb_per_split = (num_kb + best - 1) / best;
+      p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+      if (!beta) {
+        cudaError_t e = cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st);
+        if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
       }
     }
+  }
+  if (colsum && p.splits > 1 && !beta) {
+    cudaError_t e = cudaMemsetAsync(colsum, 0, (size_t)M * sizeof(float), st);
+    if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  if (colsum) {
+    if (pair) return block_n == 256 ? launch<true, true, 256, true, true>(ta, tb, td, tx, p, st) : launch<true, true, 128, true, true>(ta, tb, td, tx, p, st);
+    return block_n == 256 ? launch<true, true, 256, false, true>(ta, tb, td, tx, p, st) : launch<true, true, 128, false, true>(ta, tb, td, tx, p, st);
   }
 #define GO(AMN, BMN)                                                                                         \
   if (pair) return block_n == 256 ? launch<AMN, BMN, 256, true>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, true>(ta, tb, td, tx, p, st); \

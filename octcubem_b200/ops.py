@@ -110,6 +110,22 @@ def gemm(layout, A, B, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, aux=Non
     return out
 
 
+def wgrad_bias(dy2, x2):
+    """(dW [n_out, k_in], db [n_out]) = (dy2^T x2, column sums of dy2), both fp32.  bf16 operands: ONE tcgen05 kernel
+    (oct_gemm_wgrad_bias: the bias gradient rides on the wgrad GEMM as an extra MMA against a tile of ones); fp32 parity
+    mode: CUDA-core GEMM + the deterministic two-stage column sum."""
+    _chk(dy2, x2)
+    tokens, n_out = dy2.shape
+    k_in = x2.shape[1]
+    if dy2.dtype != torch.bfloat16:
+        return gemm(GEMM_TN, dy2, x2, n_out, k_in, tokens, torch.float32), colsum(dy2)
+    dw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy2.device)
+    db = torch.empty(n_out, dtype=torch.float32, device=dy2.device)
+    _call("oct_gemm_wgrad_bias", OCT_BF16, _p(dy2), _p(x2), _p(dw), _p(db), n_out, k_in, tokens, dy2.stride(0), x2.stride(0),
+          dw.stride(0), 0, _stream())
+    return dw, db
+
+
 def colsum(x2d, out=None, beta=0):
     _chk(x2d)
     M, N = x2d.shape
@@ -221,9 +237,11 @@ class LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm(GEMM_NN, dy2, w, M, K, N, x2.dtype).view(ctx.xshape)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            dw, db = wgrad_bias(dy2, x2)
+        elif ctx.needs_input_grad[1]:
             dw = gemm(GEMM_TN, dy2, x2, N, K, M, torch.float32)
-        if ctx.needs_input_grad[2]:
+        elif ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dw, db, None
 
@@ -256,11 +274,9 @@ class MlpFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         M = x2.shape[0]
         dpre = gemm(GEMM_NN, dy2, wb, M, hid, out_dim, x2.dtype, EPI_DGELU, aux=pre)
-        dw2 = gemm(GEMM_TN, dy2, act, out_dim, hid, M, torch.float32)
-        db2 = colsum(dy2)
+        dw2, db2 = wgrad_bias(dy2, act)
         dx = gemm(GEMM_NN, dpre, wa, M, dim, hid, x2.dtype).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        dw1 = gemm(GEMM_TN, dpre, x2, hid, dim, M, torch.float32)
-        db1 = colsum(dpre)
+        dw1, db1 = wgrad_bias(dpre, x2)
         return dx, dw1, db1, dw2, db2, None, None
 
 
@@ -395,9 +411,8 @@ class EmbedTokensFn(torch.autograd.Function):
         _call("oct_gather_tokens_bwd", _p(dout), _p(ids_keep), _p(dxk), _dt(dxk), _p(d_sp), _p(d_tmp), _p(d_cls), B, L, keep, G,
               E, _stream())
         pk = patchify(imgs, p, u, act_dtype, ids_keep=ids_keep).view(B * keep, -1)
-        dw = gemm(GEMM_TN, dxk, pk, E, pk.shape[1], B * keep, torch.float32).view(wshape)
-        db = colsum(dxk)
-        return None, dw, db, None, d_sp, d_tmp, d_cls, None, None, None
+        dw, db = wgrad_bias(dxk, pk)
+        return None, dw.view(wshape), db, None, d_sp, d_tmp, d_cls, None, None, None
 
 
 class UnshuffleFn(torch.autograd.Function):
@@ -503,9 +518,8 @@ class PatchEmbedFn(torch.autograd.Function):
         B, L, E = dx.shape
         patches = patchify(imgs, p, u, act_dtype).view(B * L, -1)
         dx2 = dx.view(B * L, E)
-        dw = gemm(GEMM_TN, dx2, patches, E, patches.shape[1], B * L, torch.float32).view(wshape)
-        db = colsum(dx2)
-        return None, dw, db, None, None, None
+        dw, db = wgrad_bias(dx2, patches)
+        return None, dw.view(wshape), db, None, None, None
 
 
 class InterpTableFn(torch.autograd.Function):

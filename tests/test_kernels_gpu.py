@@ -238,6 +238,22 @@ def test_gemm(layout, compute, M, N, K):
     assert rel(out, a.double() @ b.double().t()) < (2e-6 if K <= 8192 else 2e-5)  # fp32 accumulation over K
 
 
+@pytest.mark.parametrize("n_out,k_in,tokens", [(3072, 1024, 3280), (1024, 1024, 3280), (1536, 512, 32776), (512, 2048, 4104),
+                                               (768, 512, 8200), (200, 136, 72), (128, 128, 2000), (1024, 768, 3272)])
+def test_wgrad_bias_fused(n_out, k_in, tokens):
+    """oct_gemm_wgrad_bias: dW = dY^T X and db = column sums of dY from one kernel (pair / single CTA, split-K or not,
+    128- and 256-wide tiles, ragged M and K tails)."""
+    g = torch.Generator().manual_seed(n_out + tokens)
+    dy = torch.randn(tokens, n_out, generator=g).bfloat16()
+    x = torch.randn(tokens, k_in, generator=g).bfloat16()
+    dw, db = ops.wgrad_bias(dy.to(DEV), x.to(DEV))
+    assert dw.dtype == torch.float32 and db.dtype == torch.float32
+    assert rel(dw, dy.double().t() @ x.double()) < (2e-6 if tokens <= 8192 else 2e-5)
+    assert rel(db, dy.double().sum(0)) < 2e-6
+    dw2, db2 = ops.wgrad_bias(dy.to(DEV), x.to(DEV))  # repeatable up to the split-K reduction order
+    assert rel(dw2, dw) < 1e-6 and rel(db2, db) < 1e-6
+
+
 def test_linear_and_mlp_functions_bf16():
     g = torch.Generator().manual_seed(9)
     M, dim, hid = 300, 128, 512
