@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboctcube_b200.so")
+# OCT_LIB selects an experiment build of the same library (csrc/Makefile: BUILD= LIB= EXTRA=); never a different backend
+LIB_PATH = os.environ.get("OCT_LIB") or os.path.join(_HERE, "liboctcube_b200.so")
 
 OCT_F32, OCT_BF16, OCT_SIMT_BF16 = 0, 1, 2
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2

@@ -60,13 +60,28 @@ struct AbParams {
   int dbg;              // OCT_ATTN_BWD_DBG=16: record a cycle trace of CTA (1,0,0) (diagnostics only)
 };
 
+#ifndef OCT_AB_TRACE  // build with -DOCT_AB_TRACE=1 for the clock64 trace; the probes cost ~10 % of the issued instructions
+#define OCT_AB_TRACE 0
+#endif
+#ifndef OCT_AB_SPIN   // 1: poll the issuer <-> softmax hand-off barriers instead of suspending on them
+#define OCT_AB_SPIN 0
+#endif
+#if OCT_AB_SPIN
+#define AB_WAIT tc::mbar_wait_spin
+#else
+#define AB_WAIT tc::mbar_wait
+#endif
 __device__ long long g_ab_trace[8 * 16];
+#if !OCT_AB_TRACE
+#define AB_TRACE(id) do {} while (0)
+#else
 #define AB_TRACE(id)                                                                                              \
   do {                                                                                                           \
     if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 9 || warp == 0) && \
         i >= 8 && i < 16)                                                                                        \
       g_ab_trace[(i - 8) * 16 + (id)] = clock64();                                                               \
   } while (0)
+#endif
 
 template <int HD>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -97,7 +112,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (p.S + AB_T - 1) / AB_T;
-  const int n_sub = 2 * n_q;
+  // 64-query sub-tiles that hold at least one query: the second half of the last 128-row tile may be empty (S = 4097:
+  // 65 sub-tiles, not 66).  The dQ MMA of that tile then reads a stale (finite or zeroed) second dS^T chunk, which only
+  // reaches accumulator rows >= S that nobody reads.
+  const int n_sub = (p.S + AB_SUB - 1) / AB_SUB;
 
   if (warp == 8 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
@@ -111,6 +129,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     tc::fence_barrier_init();
   }
   if (warp == 9) tc::tmem_alloc<512>(tmem_slot);
+  if ((n_sub & 1) && warp < 8) {  // never-written half of the last tile's dS^T buffer (read by its dQ MMA, see above)
+    uint4* z = reinterpret_cast<uint4*>(sDS + ((n_q - 1) & 1) * C::kDsBytes + 128 * 128);
+    for (int i = threadIdx.x; i < 128 * 128 / 16; i += AB_SM_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();
+  }
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -184,7 +207,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         const uint32_t off = qstage * kStageStep + hh * kHalfStep;
         const uint32_t tcol = tmem_base + st * C::kStageCols;
         AB_TRACE(0);
-        tc::mbar_wait(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
+        AB_WAIT(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
         tc::tcgen05_fence_after();
         AB_TRACE(1);
         if (tc::elect_one()) {
@@ -196,10 +219,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         for (int k = 0; k < AB_SUB / 16; ++k)  // dK += dS^T Q_h
           tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
                      (i | k) != 0);
-        if (hh == 1) tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves issued earlier)
+        if (hh == 1 || i == n_sub - 1) tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves issued earlier)
         }
         __syncwarp();
-        if (hh == 1) {
+        if (hh == 1 || i == n_sub - 1) {
           if (m > 0) {
             tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM
             tc::tcgen05_fence_after();
@@ -297,7 +320,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
       const uint32_t tcol = lane_addr + st * C::kStageCols + colhalf * 32;
       AB_TRACE(4);
-      tc::mbar_wait(&sdp_full[st], (i >> 1) & 1);
+      AB_WAIT(&sdp_full[st], (i >> 1) & 1);
       tc::tcgen05_fence_after();
       AB_TRACE(5);
       uint32_t s[32], dp[32];
@@ -358,12 +381,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       if (hh == 1 && m > 0) drain_dq(m - 1, i);
       AB_TRACE(9);
     }
+    if ((n_sub & 1) && n_q > 1) drain_dq(n_q - 2, 0);  // its deferred slot (second half of the last tile) does not exist
     drain_dq(n_q - 1, 0);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#if OCT_AB_TRACE
     if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
       for (int i = 0; i < 8; ++i)
         for (int k = 0; k < 14; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
     }
+#endif
     // epilogue: column half 0 stores dV, half 1 stores dK of this kv tile
     tc::mbar_wait(acc_full, 0);
     tc::tcgen05_fence_after();

@@ -18,6 +18,18 @@
 // keep the SFU pipe busy.  head_dim 64 uses 128B swizzle, head_dim 32 uses 64B swizzle (TMA row pitch = inner box extent).
 #include "tc_common.cuh"
 
+#ifndef OCT_AT_POLY_EVERY  // one exponential pair in OCT_AT_POLY_EVERY is evaluated on the FMA pipe (0 = none)
+#define OCT_AT_POLY_EVERY 4
+#endif
+#ifndef OCT_AT_SPIN        // 1: poll the issuer <-> softmax hand-off barriers instead of suspending on them
+#define OCT_AT_SPIN 0
+#endif
+#if OCT_AT_SPIN
+#define AT_WAIT tc::mbar_wait_spin
+#else
+#define AT_WAIT tc::mbar_wait
+#endif
+
 namespace {
 
 constexpr int AT_BM = 128, AT_BN = 128, AT_QT = 2, AT_THREADS = 64 + AT_QT * 128, AT_KV_STAGES = 4, AT_SBUFS = 3;
@@ -100,7 +112,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
   // exp2_poly2 on the FMA pipe: the loop is bound by MUFU.EX2 (16 / clk / SM), so moving a quarter of the exponentials
   // off the SFU shortens it (same idea as FlashAttention-4's software exp2).  The masked tile keeps the SFU for all
   // columns so that -inf stays exactly 0.
-  constexpr int kPolyEvery = 4;
+  constexpr int kPolyEvery = OCT_AT_POLY_EVERY;
   const uint64_t sc2 = tc::pack2(scale_log2e, scale_log2e), nm2 = tc::pack2(-m, -m);
   uint64_t la = tc::pack2(0.f, 0.f), lb = la;
 #pragma unroll
@@ -110,7 +122,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
     for (int i = 0; i < 16; ++i) {
       const uint64_t x = tc::fma2(tc::pack2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])), sc2, nm2);
       float p0, p1;
-      if (!kMasked && (i % kPolyEvery) == kPolyEvery - 1) {
+      if (!kMasked && kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
         tc::exp2_poly2(x, p0, p1);
       } else {
         float x0, x1;
@@ -152,6 +164,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (AT_QT * AT_BM), h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.S + AT_BN - 1) / AT_BN;
+  // The last CTA of a (batch, head) may own a single live Q tile (S = 4097: one query row in the 17th CTA); then score
+  // tile n is simply kv tile n of Q tile 0 and warpgroup 1 idles, instead of sweeping the keys for 128 rows that do not exist.
+  const int qsh = (q0 + AT_BM < p.S) ? 1 : 0;  // log2(number of live Q tiles): tile n -> (t = n & qsh, j = n >> qsh)
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
@@ -193,8 +208,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     {
       constexpr uint32_t idesc_qk = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, AT_BN);
       constexpr uint32_t idesc_pv = tc::make_idesc(tc::kFmtBF16, false, true, AT_BM, HD);
-      auto issue_qk = [&](int n) {  // score tile n: Q tile n & 1 against K_(n >> 1)
-        const int t = n & 1, stage = (n >> 1) % AT_KV_STAGES;
+      auto issue_qk = [&](int n) {  // score tile n: Q tile n & qsh against K_(n >> qsh)
+        const int t = n & qsh, stage = (n >> qsh) % AT_KV_STAGES;
         const uint32_t q_addr = tc::smem_u32(sQ + t * C::kTileBytes);
         const uint32_t k_addr = tc::smem_u32(sK + stage * C::kTileBytes);
         const uint32_t d_addr = tmem_base + C::kColS + (n % AT_SBUFS) * 128;
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
         tc::mma_commit(&s_full[n % AT_SBUFS]);
       };
       auto issue_pv = [&](int n) {
-        const int t = n & 1, j = n >> 1, stage = j % AT_KV_STAGES;
+        const int t = n & qsh, j = n >> qsh, stage = j % AT_KV_STAGES;
         const uint32_t v_addr = tc::smem_u32(sV + stage * C::kTileBytes);
         const uint32_t p_addr = tmem_base + C::kColS + (n % AT_SBUFS) * 128;
 #pragma unroll
@@ -222,32 +237,36 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
         tc::mbar_wait(&kv_full[j % AT_KV_STAGES], (j / AT_KV_STAGES) & 1);
         tc::tcgen05_fence_after();
       };
-      const int n_tiles = 2 * n_kv;
+      const int n_tiles = n_kv << qsh;
+      // Score tiles are issued `ahead` tiles in front of their PV.  o_done[t] is only waited on when O must be rescaled, so
+      // the barrier must never get two phases ahead of its waiter (the parity wait would alias): s_full(n) implies
+      // PV(n - ahead) is complete, i.e. this warpgroup's PV(j - 2) with two live Q tiles and ahead = 3; with a single live
+      // Q tile every PV belongs to warpgroup 0, hence ahead = 2 there.
+      const int ahead = 2 + qsh;
       tc::mbar_wait(q_full, 0);
-      wait_kv(0);
-      if (n_kv > 1) wait_kv(1);
+      const int n_pro = min(ahead, n_tiles);
+      for (int n = 0; n < n_pro; ++n)
+        if ((n & qsh) == 0) wait_kv(n >> qsh);
       if (tc::elect_one()) {
-        issue_qk(0);
-        issue_qk(1);
-        if (n_kv > 1) issue_qk(2);
+        for (int n = 0; n < n_pro; ++n) issue_qk(n);
       }
       __syncwarp();
       for (int n = 0; n < n_tiles; ++n) {
-        const int t = n & 1, j = n >> 1;
-        tc::mbar_wait(&p_full[n % AT_SBUFS], (n / AT_SBUFS) & 1);  // P(n) in TMEM (and O_t rescaled if needed)
+        const int t = n & qsh, j = n >> qsh;
+        AT_WAIT(&p_full[n % AT_SBUFS], (n / AT_SBUFS) & 1);  // P(n) in TMEM (and O_t rescaled if needed)
         tc::tcgen05_fence_after();
-        const bool more = n + AT_SBUFS < n_tiles;
-        if (more && ((n + AT_SBUFS) & 1) == 0) wait_kv((n + AT_SBUFS) >> 1);
+        const bool more = n + ahead < n_tiles;
+        if (more && ((n + ahead) & qsh) == 0) wait_kv((n + ahead) >> qsh);
         if (tc::elect_one()) {
           issue_pv(n);
-          if (t == 1) tc::mma_commit(&kv_empty[j % AT_KV_STAGES]);  // K_j, V_j fully consumed
-          if (more) issue_qk(n + AT_SBUFS);  // into the buffer PV(n) reads: ordered behind it on the tensor pipe
+          if (t == qsh) tc::mma_commit(&kv_empty[j % AT_KV_STAGES]);  // K_j, V_j fully consumed (by the last live Q tile)
+          if (more) issue_qk(n + ahead);  // into the buffer PV(n) (or PV(n - 1)) has read: ordered behind it on the tensor pipe
         }
         __syncwarp();
       }
     }
     __syncwarp();
-  } else {
+  } else if (((warp - 2) >> 2) <= qsh) {
     // ===================== softmax / correction / epilogue: warpgroup t owns Q tile t =====================
     const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
@@ -256,8 +275,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     const uint32_t tmem_o = lane_addr + C::kColO + t * HD;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      const int n = 2 * j + t, buf = n % AT_SBUFS;
-      tc::mbar_wait(&s_full[buf], (n / AT_SBUFS) & 1);
+      const int n = (j << qsh) + t, buf = n % AT_SBUFS;
+      AT_WAIT(&s_full[buf], (n / AT_SBUFS) & 1);
       tc::tcgen05_fence_after();
       const int valid = p.S - j * AT_BN;  // columns >= valid are out of range (TMA zero-filled K rows)
       const uint32_t tmem_s = lane_addr + C::kColS + buf * 128;
