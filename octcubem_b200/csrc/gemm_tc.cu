@@ -82,11 +82,13 @@ constexpr int kOnesBytes = 16 * 128;  // [16 rows x 64 bf16] tile of ones: B ope
 // TMEM columns behind a SINGLE accumulator stage (2 x 256 + 16 columns do not fit the 512-column TMEM).  It replaces a
 // separate pass over dY per nn.Linear (131 column-sum launches, 5.5 % of the step, profiles/r1_step_launches.md);
 // wgrad-shaped problems map one work item to each CTA, so the second accumulator stage was idle there anyway.
-template <int BLOCK_N, bool kColsum>
+template <int BLOCK_N, bool kColsum, bool kPair>
 struct Cfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 3 : (kColsum ? 4 : 5);  // 144 / 160 KB of operands + 64 KB of output staging
+  // a CTA of a pair keeps only ITS half of the B tile (the 2-CTA MMA reads the other half from the peer's smem)
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
+  // operand ring + 64 KB of output staging (+ 2 KB ones tile) within 227 KB
+  static constexpr int kStages = kPair ? (kColsum ? 4 : 5) : ((BLOCK_N == 256) ? 3 : (kColsum ? 4 : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAccStages = kColsum ? 1 : 2;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages, or one + the colsum columns (power of two: 256 or 512)
@@ -110,19 +112,23 @@ struct GemmParams {
   float* colsum;     // kColsum: [M] fp32, (+)= column sums of the MN-major A operand (the bias gradient of a wgrad)
 };
 
-// kPair: the grid is launched in clusters of two CTAs that work on vertically adjacent 128-row tiles of the same
-// 256-column strip.  Each CTA fetches only HALF of the shared B tile and TMA-multicasts it into both CTAs' smem, so the
-// L2 -> SM operand traffic per MMA drops from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2-bandwidth-bound at
-// ~26 TB/s demand, profiles/r1_gemm_ncu.md).  A stage may only be refilled once BOTH CTAs' MMAs have consumed it,
-// hence the multicast tcgen05.commit onto both empty barriers (arrival count 2).
+// kPair: the grid is launched in clusters of two CTAs (one TPC) that own vertically adjacent 128-row tiles of the same
+// 256-column strip and run ONE tcgen05.mma.cta_group::2 (M = 256) per k-step, issued by the even ("leader") CTA.  Each CTA
+// stages its own 128 rows of A and only ITS HALF of the B tile (32 KB per k-block instead of 48 KB): with single-CTA
+// MMAs the operand ring needs 96 B/clk of smem writes (TMA) plus 96 B/clk of reads (MMA) against a 128 B/clk port, which
+// capped the main loop at ~65 % of the tensor rate (36.6 us for the 3280x1024x4096 fc2 tile, profiles/r1_step_launches.md).
+// Protocol: both CTAs' TMA loads complete on the LEADER's full barrier (which the leader arms with the bytes of both);
+// the leader's tcgen05.commit multicasts onto both CTAs' empty / tmem_full barriers; the epilogue warps of both CTAs
+// release an accumulator stage on the leader's tmem_empty barrier (one arrival per warp).
 template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair, bool kColsum>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                               const __grid_constant__ CUtensorMap tmap_b,
                                                               const __grid_constant__ CUtensorMap tmap_d,
                                                               const __grid_constant__ CUtensorMap tmap_aux,
                                                               const GemmParams p) {
-  using C = Cfg<BLOCK_N, kColsum>;
+  using C = Cfg<BLOCK_N, kColsum, kPair>;
   static_assert(!kColsum || A_MN, "the bias-gradient MMA sums the MN-major A operand over K");
+  static_assert(!kPair || BLOCK_N == 256, "pair mode: 256 x 256 output tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -155,16 +161,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tc::prefetch_tmap(&tmap_d);
     for (int s = 0; s < C::kStages; ++s) {
       tc::mbar_init(&full_bar[s], 1);
-      tc::mbar_init(&empty_bar[s], kPair ? 2 : 1);
+      tc::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tmem_full[s], 1);
-      tc::mbar_init(&tmem_empty[s], kEpiThreads);
+      tc::mbar_init(&tmem_empty[s], kPair ? 2 * (kEpiThreads / 32) : kEpiThreads);  // pair: one arrival per epilogue warp of both CTAs
     }
     for (int s = 0; s < 4; ++s) tc::mbar_init(&aux_full[s], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  if (warp == 1) {
+    if (kPair) tc::tmem_alloc_pair<C::kTmemCols>(tmem_base_slot); else tc::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  }
   if (kColsum) {
     for (int i = threadIdx.x; i < kOnesBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem_ones)[i] = 0x3F803F80u;
     tc::fence_proxy_async();  // generic-proxy stores -> tcgen05.mma operand reads
@@ -196,18 +204,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int kb0 = (w / num_tiles) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-          tc::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           uint8_t* sa = smem_a + stage * C::kABytes;
           uint8_t* sb = smem_b + stage * C::kBBytes;
           const int k0 = kb * BLOCK_K;
-          if (!A_MN) {
-            tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
-          } else {
-#pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              tc::tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + c * 64, k0);
-          }
           if (!kPair) {
+            tc::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            if (!A_MN) {
+              tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tc::tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + c * 64, k0);
+            }
             if (!B_MN) {
               tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
             } else {
@@ -215,15 +223,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               for (int c = 0; c < BLOCK_N / 64; ++c)
                 tc::tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0);
             }
-          } else {  // my half of the B tile, delivered to both CTAs of the pair
-            if (!B_MN) {
-              tc::tma_load_2d_mc(sb + rank * (BLOCK_N / 2) * 128, &tmap_b, &full_bar[stage], k0, n0 + rank * (BLOCK_N / 2), 3);
+          } else {
+            // the leader arms its full barrier with the bytes of BOTH CTAs; every load of the pair completes there
+            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            if (!A_MN) {
+              tc::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], k0, m0);
             } else {
 #pragma unroll
-              for (int cc = 0; cc < BLOCK_N / 128; ++cc) {
-                const int c = rank * (BLOCK_N / 128) + cc;
-                tc::tma_load_2d_mc(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0, 3);
-              }
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tc::tma_load_2d_pair(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + c * 64, k0);
+            }
+            const int nh = n0 + rank * (BLOCK_N / 2);  // my half of the B tile's N rows
+            if (!B_MN) {
+              tc::tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], k0, nh);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 128; ++c)
+                tc::tma_load_2d_pair(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], nh + c * 64, k0);
             }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -232,15 +248,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = tc::make_idesc(tc::kFmtBF16, A_MN, B_MN, BLOCK_M, BLOCK_N);
-    constexpr uint32_t idesc_cs = tc::make_idesc(tc::kFmtBF16, A_MN, false, BLOCK_M, 16);  // A^T x ones[16 x K] (K-major)
+    constexpr int kMmaM = kPair ? 2 * BLOCK_M : BLOCK_M;  // cta_group::2: one instruction covers both CTAs' rows
+    constexpr uint32_t idesc = tc::make_idesc(tc::kFmtBF16, A_MN, B_MN, kMmaM, BLOCK_N);
+    constexpr uint32_t idesc_cs = tc::make_idesc(tc::kFmtBF16, A_MN, false, kMmaM, 16);  // A^T x ones[16 x K] (K-major)
     const uint64_t d_ones = tc::make_smem_desc(tc::smem_u32(smem_ones), 16, 1024);         // every k-slice is all ones
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = cta; w < num_work; w += ncta) {
-      if (lane == 0) {
+      if (lane == 0 && rank == 0) {  // pair: the peer's warp 1 only allocates / frees TMEM
         bool with_colsum = false;
         if (kColsum) {  // the n-block-0 tile of every m-block row carries the column sums of its A tiles
           int m_blk, n_blk;
@@ -263,14 +280,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                      : tc::make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? tc::make_smem_desc(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : tc::make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
-            tc::mma_ss(tmem_d, da, db, idesc, (kb | k) != 0);
-            if (kColsum && with_colsum) tc::mma_ss(tmem_base + C::kColsumCol, da, d_ones, idesc_cs, (kb | k) != 0);
+            if (kPair) {
+              tc::mma_ss_pair(tmem_d, da, db, idesc, (kb | k) != 0);
+              if (kColsum && with_colsum) tc::mma_ss_pair(tmem_base + C::kColsumCol, da, d_ones, idesc_cs, (kb | k) != 0);
+            } else {
+              tc::mma_ss(tmem_d, da, db, idesc, (kb | k) != 0);
+              if (kColsum && with_colsum) tc::mma_ss(tmem_base + C::kColsumCol, da, d_ones, idesc_cs, (kb | k) != 0);
+            }
           }
-          // frees the smem slot once these MMAs have read it (in both CTAs of a pair: the peer multicasts into it)
-          if (kPair) tc::mma_commit_mc(&empty_bar[stage], 3); else tc::mma_commit(&empty_bar[stage]);
+          // frees the smem slot once these MMAs have read it (pair: in both CTAs)
+          if (kPair) tc::mma_commit_pair(&empty_bar[stage], 3); else tc::mma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: of both CTAs)
+        if (kPair) tc::mma_commit_pair(&tmem_full[acc], 3); else tc::mma_commit(&tmem_full[acc]);
       }
       __syncwarp();
       if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -288,6 +311,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     int stg_sel = 0;
     const int bar_id = 1 + colhalf;
     const bool issuer = (quarter == 0) && (lane == 0);
+    // hand an accumulator stage back to the MMA issuer: every thread (single CTA), or one arrival per warp on the LEADER's
+    // barrier (pair; the peer arrives remotely)
+    const uint32_t tmem_empty_leader[2] = {kPair ? tc::mapa_u32(&tmem_empty[0], 0) : 0u, kPair ? tc::mapa_u32(&tmem_empty[1], 0) : 0u};
+    auto release_acc = [&](int a) {
+      tc::tcgen05_fence_before();
+      if (!kPair) {
+        tc::mbar_arrive(&tmem_empty[a]);
+      } else {
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_cluster(tmem_empty_leader[a]);
+      }
+    };
     // 128-byte row segment (32 x 32-bit) -> staging tile -> TMA store of the [128 rows x 128 B] group at (col, row0)
     auto stage_and_store = [&](const uint32_t (&o)[32], const CUtensorMap* map, int col, int row0, bool reduce_add) {
       uint8_t* stg = stg_base + stg_sel * kEpiStageBytes;
@@ -356,10 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tc::tmem_ld_x32(taddr + g * 64, r0);
           tc::tmem_ld_x32(taddr + g * 64 + 32, r1);
           tc::tmem_ld_wait();
-          if (gg == kGroups - 1 || nc + 64 >= p.N) {  // last TMEM read of this tile: hand the accumulator back
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(&tmem_empty[acc]);
-          }
+          if (gg == kGroups - 1 || nc + 64 >= p.N) release_acc(acc);  // last TMEM read of this tile
           float v[64];
 #pragma unroll
           for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
@@ -426,10 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           uint32_t o[32];
           tc::tmem_ld_x32(taddr + g * 32, o);
           tc::tmem_ld_wait();
-          if (gg == kGroups - 1 || nc + 32 >= p.N) {
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(&tmem_empty[acc]);
-          }
+          if (gg == kGroups - 1 || nc + 32 >= p.N) release_acc(acc);
           if (p.epilogue == OCT_EPI_BIAS) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -447,10 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
       // a tile whose column half lies entirely beyond N never reached an arrive above
-      if (n0 + colhalf * (BLOCK_N / 2) >= p.N) {
-        tc::tcgen05_fence_before();
-        tc::mbar_arrive(&tmem_empty[acc]);
-      }
+      if (n0 + colhalf * (BLOCK_N / 2) >= p.N) release_acc(acc);
       if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have left smem and are visible
@@ -461,14 +487,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (kPair) tc::cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc::tcgen05_fence_after();
-    tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+    if (kPair) tc::tmem_dealloc_pair<C::kTmemCols>(tmem_base); else tc::tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
 template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair, bool kColsum = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx, const GemmParams& p,
            cudaStream_t st) {
-  using C = Cfg<BLOCK_N, kColsum>;
+  using C = Cfg<BLOCK_N, kColsum, kPair>;
   auto kern = gemm_tc_kernel<A_MN, B_MN, BLOCK_N, kPair, kColsum>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
@@ -534,8 +560,8 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   CUtensorMap ta, tb;
   int rc = make_operand_map(&ta, A, a_mn, M, K, lda, BLOCK_M, "oct_gemm(bf16) A");
   if (rc) return rc;
-  // pair mode (2-CTA clusters sharing B through TMA multicast) whenever there are at least two m-blocks
-  const bool pair = (M > BLOCK_M) && (getenv("OCT_GEMM_NO_PAIR") == nullptr);
+  // pair mode (2-CTA clusters running cta_group::2 MMAs on 256 x 256 tiles) whenever there are at least two m-blocks
+  const bool pair = (M > BLOCK_M) && block_n == 256 && (getenv("OCT_GEMM_NO_PAIR") == nullptr);
   rc = make_operand_map(&tb, B, b_mn, N, K, ldb, pair ? block_n / 2 : block_n, "oct_gemm(bf16) B");
   if (rc) return rc;
   // output maps for the TMA-store epilogue: [M, N] row-major, one box = 128 rows x 128 bytes
@@ -594,11 +620,11 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
     if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
   }
   if (colsum) {
-    if (pair) return block_n == 256 ? launch<true, true, 256, true, true>(ta, tb, td, tx, p, st) : launch<true, true, 128, true, true>(ta, tb, td, tx, p, st);
+    if (pair) return launch<true, true, 256, true, true>(ta, tb, td, tx, p, st);
     return block_n == 256 ? launch<true, true, 256, false, true>(ta, tb, td, tx, p, st) : launch<true, true, 128, false, true>(ta, tb, td, tx, p, st);
   }
 #define GO(AMN, BMN)                                                                                         \
-  if (pair) return block_n == 256 ? launch<AMN, BMN, 256, true>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, true>(ta, tb, td, tx, p, st); \
+  if (pair) return launch<AMN, BMN, 256, true>(ta, tb, td, tx, p, st);                                   \
   return block_n == 256 ? launch<AMN, BMN, 256, false>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, false>(ta, tb, td, tx, p, st)
   switch (layout) {
     case OCT_GEMM_NT: GO(false, false);
