@@ -561,7 +561,9 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   int rc = make_operand_map(&ta, A, a_mn, M, K, lda, BLOCK_M, "oct_gemm(bf16) A");
   if (rc) return rc;
   // pair mode (2-CTA clusters running cta_group::2 MMAs on 256 x 256 tiles) whenever there are at least two m-blocks
-  const bool pair = (M > BLOCK_M) && block_n == 256 && (getenv("OCT_GEMM_NO_PAIR") == nullptr);
+  // ... and the contraction is long enough for the main loop to matter: at K <= 512 (8 k-blocks per tile) the tile time is
+  // the epilogue's, and the pair's cross-CTA accumulator hand-off only adds latency (tools/time_gemm_shapes.py)
+  const bool pair = (M > BLOCK_M) && block_n == 256 && K > 512 && (getenv("OCT_GEMM_NO_PAIR") == nullptr);
   rc = make_operand_map(&tb, B, b_mn, N, K, ldb, pair ? block_n / 2 : block_n, "oct_gemm(bf16) B");
   if (rc) return rc;
   // output maps for the TMA-store epilogue: [M, N] row-major, one box = 128 rows x 128 bytes
