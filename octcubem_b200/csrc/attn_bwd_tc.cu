@@ -19,16 +19,21 @@
 //   * bf16 P^T / dS^T overwrite the fp32 columns their own thread has consumed (no extra columns, no cross-warp hazard);
 //   * the dS^T smem tile is double-buffered and the dQ drain of tile m is deferred by one sub-tile, so the threads
 //     never stall on the tail of the queue.
-// 320 threads: warps 0-7 softmax-backward (two warps per TMEM lane quarter, 32 query columns each -> two warps per
-// scheduler hide each other's TMEM / SFU latency), warp 8 TMA producer, warp 9 MMA issuer (highest warp id: the
-// scheduler arbitrates highest-id first and everything waits on this serial chain).
+// 512 threads in four warpgroups: warps 0-7 softmax-backward (two warps per TMEM lane quarter, 32 query columns each ->
+// two warps per scheduler hide each other's TMEM / SFU latency), warp 8 TMA producer, warp 9 MMA issuer, warps 12-15 drain
+// the dQ tiles (TMEM -> smem -> bulk reduction).  The softmax warps are the critical path of the kernel (clock64 trace:
+// they are never idle, the issuer waits for them 30-50 % of the time), so everything that is not exp / multiply / convert
+// is kept off them; draining dQ cost them ~12 % of every query tile.  setmaxnreg moves the registers of the light
+// warpgroups to the softmax warpgroups.
 #include "tc_common.cuh"
 #include <type_traits>
 #include <cstdlib>
 
 namespace {
 
-constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 320, AB_SM_THREADS = 256, AB_Q_STAGES = 2;
+constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 512, AB_SM_THREADS = 256, AB_DRAIN_THREADS = 128, AB_Q_STAGES = 2;
+// register budget (setmaxnreg, per warpgroup): 8 softmax warps x 176 + 8 control / drain warps x 80 = 64 K registers
+constexpr int AB_REGS_SOFTMAX = 176, AB_REGS_OTHER = 80;
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int HD>
@@ -105,7 +110,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint64_t* sdp_full = q_empty + AB_Q_STAGES;  // [2] per fp32 stage, one completion every other sub-tile
   uint64_t* p_ready = sdp_full + 2;            // [2] per fp32 stage (256 arrivals)
   uint64_t* dq_full = p_ready + 2;             // once per query tile
-  uint64_t* dq_free = dq_full + 1;             // once per query tile (256 arrivals)
+  uint64_t* dq_free = dq_full + 1;             // once per query tile (the 128 drain threads)
   uint64_t* acc_full = dq_free + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
@@ -124,7 +129,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     for (int s = 0; s < AB_Q_STAGES; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&sdp_full[s], 1); tc::mbar_init(&p_ready[s], AB_SM_THREADS); }
     tc::mbar_init(dq_full, 1);
-    tc::mbar_init(dq_free, AB_SM_THREADS);
+    tc::mbar_init(dq_free, AB_DRAIN_THREADS);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
   }
@@ -139,6 +144,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // setmaxnreg sits at the top of each role's branch: ptxas budgets the registers of a region by the setmaxnreg that
+  // dominates it (after a common if / else it applies the smaller value to everything that follows).
+  if (warp >= 8 && warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_OTHER));
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -248,8 +257,50 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       if (tc::elect_one()) tc::mma_commit(acc_full);
     }
     __syncwarp();
+  }
+  } else if (warp >= 12) {
+    // ===================== dQ drain: warp 12 + q owns TMEM lane quarter q =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_OTHER));
+    // TMEM -> registers -> per-warp smem block -> ONE asynchronous bulk reduction of that block into the fp32 accumulator.
+    // Accumulator layout per 128-query tile: [lane quarter][16-byte chunk][32 rows][4 floats] (attn_dq_convert_kernel
+    // undoes it): contiguous per warp, and the st.shared.v4 of a warp hit 32 different bank groups.
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const size_t bh = (size_t)b * p.H + h;
+    constexpr int kWarpDqBytes = 32 * HD * 4;  // 32 rows x HD columns fp32
+    uint8_t* sdq_w = sDQ + quarter * kWarpDqBytes;
+    for (int m = 0; m < n_q; ++m) {
+      tc::mbar_wait(dq_full, m & 1);
+      tc::tcgen05_fence_after();
+      uint32_t o[HD];
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t(&oc)[32] = reinterpret_cast<uint32_t(&)[32]>(o[c * 32]);
+        tc::tmem_ld_x32(lane_addr + C::kColDQ + c * 32, oc);
+      }
+      tc::tmem_ld_wait();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(dq_free);  // dQ is in registers: the issuer may overwrite the TMEM tile
+      // this warp's bulk reduction of the previous query tile must have finished reading its staging block
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < HD / 4; ++q)
+        *reinterpret_cast<uint4*>(sdq_w + (q * 32 + lane) * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD + quarter * (kWarpDqBytes / 4);
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                     "r"(tc::smem_u32(sdq_w)), "r"((uint32_t)kWarpDqBytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ===================== softmax-backward threads: (kv row, 32 query columns) per sub-tile =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AB_REGS_SOFTMAX));
     const int quarter = warp & 3, colhalf = warp >> 2;
     const int row = quarter * 32 + lane;  // kv row inside the tile == TMEM lane
     const int tid = threadIdx.x;          // 0..255
@@ -266,45 +317,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const size_t idx = bh * p.S + min(stat_q(i), p.S - 1);
       a = p.lse[idx];
       d = p.delta[idx];
-    };
-    // TMEM -> registers -> per-warp smem block -> ONE asynchronous bulk reduction of that block into the fp32 accumulator.
-    // Accumulator layout per 128-query tile: [warp][16-byte chunk][32 rows][4 floats] (attn_dq_convert_kernel undoes it):
-    // contiguous per warp, and the st.shared.v4 of a warp hit 32 different bank groups.
-    constexpr int kWarpDqBytes = HD * 64;  // 32 rows x HD/2 columns fp32
-    uint8_t* sdq_w = sDQ + warp * kWarpDqBytes;
-    auto drain_dq = [&](int m, int i) {
-      tc::mbar_wait(dq_full, m & 1);
-      tc::tcgen05_fence_after();
-      AB_TRACE(10);
-      uint32_t o[HD / 2];
-      if (HD == 32) {
-        uint32_t(&o16)[16] = reinterpret_cast<uint32_t(&)[16]>(o);
-        tc::tmem_ld_x16(lane_addr + C::kColDQ + colhalf * 16, o16);
-      } else {
-        uint32_t(&o32)[32] = reinterpret_cast<uint32_t(&)[32]>(o);
-        tc::tmem_ld_x32(lane_addr + C::kColDQ + colhalf * 32, o32);
-      }
-      tc::tmem_ld_wait();
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(dq_free);  // dQ columns are in registers: the issuer may overwrite the TMEM tile
-      AB_TRACE(11);
-      // this warp's bulk reduction of the previous query tile must have finished reading its staging block
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      AB_TRACE(12);
-#pragma unroll
-      for (int q = 0; q < HD / 8; ++q)
-        *reinterpret_cast<uint4*>(sdq_w + (q * 32 + lane) * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-      tc::fence_proxy_async();
-      __syncwarp();
-      AB_TRACE(13);
-      if (lane == 0) {
-        float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD + warp * (kWarpDqBytes / 4);
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                     "r"(tc::smem_u32(sdq_w)), "r"((uint32_t)kWarpDqBytes)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
     };
     float raw_lse, raw_delta;
     ld_stat(0, raw_lse, raw_delta);
@@ -374,16 +386,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&p_ready[st]);
       AB_TRACE(8);
-      // deferred drain: dQ of the previous query tile was queued TWO sub-tiles ago.  One sub-tile was not enough: its
-      // eight MN-major SS MMAs (~130 clk each) run behind dV/dK of the same iteration, and these warps — the critical
-      // path of the kernel — sat ~470 clk per query tile in the dq_full wait (clock64 trace, profiles/r1_attention_ncu.md).
-      // The issuer waits for dq_free right after this sub-tile's p_ready, so the drain costs it ~200 clk of its slack.
-      if (hh == 1 && m > 0) drain_dq(m - 1, i);
       AB_TRACE(9);
     }
-    if ((n_sub & 1) && n_q > 1) drain_dq(n_q - 2, 0);  // its deferred slot (second half of the last tile) does not exist
-    drain_dq(n_q - 1, 0);
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #if OCT_AB_TRACE
     if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
       for (int i = 0; i < 8; ++i)
@@ -459,11 +463,11 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bf
   const int hh = (int)(r % H); r /= H;
   const int s = (int)(r % S);
   const int64_t bb = r / S;
-  // accumulator layout per 128-query tile: [warp = 4 * column half + row quarter][chunk][32 rows][4 floats]
-  // (see the per-warp drain in attn_bwd_tc_kernel)
-  const int rr = s & 127, wq = (c4 / (HD / 8)) * 4 + (rr >> 5), q = c4 % (HD / 8);
+  // accumulator layout per 128-query tile: [row quarter][16-byte chunk][32 rows][4 floats] (see the drain warps of
+  // attn_bwd_tc_kernel)
+  const int rr = s & 127;
   const float4 v = *reinterpret_cast<const float4*>(dq_acc + ((bb * H + hh) * Spad + (s & ~127)) * HD +
-                                                    ((wq * (HD / 8) + q) * 32 + (rr & 31)) * 4);
+                                                    (((rr >> 5) * (HD / 4) + c4) * 32 + (rr & 31)) * 4);
   __nv_bfloat16* dst = dqkv + (((bb * S + s) * 3 + 0) * H + hh) * HD + c4 * 4;
   Vec4<__nv_bfloat16>::st(dst, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
 }
