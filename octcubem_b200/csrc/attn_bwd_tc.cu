@@ -216,42 +216,38 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         const uint32_t off = qstage * kStageStep + hh * kHalfStep;
         const uint32_t tcol = tmem_base + st * C::kStageCols;
         AB_TRACE(0);
+        // This warp is the critical path once the softmax warps have slack (clock64 trace: ~45-65 clk per issued MMA,
+        // the tensor pipe streams a 128x16 A operand per instruction whatever N is): all waits first, then ONE elected
+        // region.  Order G(i) -> S/dP(i+2) -> dQ(m): the scores the softmax warps wait for are not queued behind dQ,
+        // which only the drain warps need.
+        const bool dq_now = (hh == 1) || (i == n_sub - 1);
         AB_WAIT(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
+        if (i + 2 < n_sub) wait_q(i + 2);
+        if (dq_now && m > 0) tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM (long ago)
         tc::tcgen05_fence_after();
         AB_TRACE(1);
         if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AB_SUB / 16; ++k)  // dV += P^T dO_h
-          tc::mma_ts(tmem_base + C::kColDV, tcol + C::kColST + C::slice_off(k), dDO0_mn + off + k * kKStepMN, idesc_acc,
-                     (i | k) != 0);
+          for (int k = 0; k < AB_SUB / 16; ++k)  // dV += P^T dO_h
+            tc::mma_ts(tmem_base + C::kColDV, tcol + C::kColST + C::slice_off(k), dDO0_mn + off + k * kKStepMN, idesc_acc,
+                       (i | k) != 0);
 #pragma unroll
-        for (int k = 0; k < AB_SUB / 16; ++k)  // dK += dS^T Q_h
-          tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
-                     (i | k) != 0);
-        if (hh == 1 || i == n_sub - 1) tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves issued earlier)
-        }
-        __syncwarp();
-        if (hh == 1 || i == n_sub - 1) {
-          if (m > 0) {
-            tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM
-            tc::tcgen05_fence_after();
-          }
-          if (tc::elect_one()) {
+          for (int k = 0; k < AB_SUB / 16; ++k)  // dK += dS^T Q_h
+            tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
+                       (i | k) != 0);
+          if (dq_now) tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves issued earlier)
+          // scores of sub-tile i+2 reuse fp32 stage st: queued behind the MMAs above, which read its bf16 contents
+          if (i + 2 < n_sub) issue_sdp(i + 2);
+          AB_TRACE(2);
+          if (dq_now) {
             const uint32_t dsoff = (m & 1) * kDsBufStep;
 #pragma unroll
             for (int k = 0; k < 128 / 16; ++k)  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
               tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + dsoff + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
             tc::mma_commit(dq_full);
           }
-          __syncwarp();
         }
-        AB_TRACE(2);
-        // scores of sub-tile i+2 reuse fp32 stage st: queued behind the MMAs above, which read its bf16 contents
-        if (i + 2 < n_sub) {
-          wait_q(i + 2);
-          if (tc::elect_one()) issue_sdp(i + 2);
-          __syncwarp();
-        }
+        __syncwarp();
         AB_TRACE(3);
       }
       if (tc::elect_one()) tc::mma_commit(acc_full);
