@@ -3,6 +3,7 @@
 //                        final norms models_mae_joint_res_flash_attn.py:489,592
 // One warp owns one row; the row lives in registers between the statistics passes (read once, written once).
 #include "common.cuh"
+#include <cstdlib>
 
 constexpr int kLnWarps = 4;  // warps per CTA
 
@@ -199,6 +200,128 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const TDY* __
   }
 }
 
+// ---- pipelined variant for C = 128 * NV * WPR (the model's 512 / 1024 and the toy widths) -------------------------
+// The kernel above keeps ~16 rows per SM in flight but every warp alternates "load, reduce, load dres, store", so its
+// loads are outstanding only about half of the time: 3.4 TB/s at the decoder shape (profiles/r1_step_launches.md).
+// Here a row is owned by WPR warps (NV float4 per lane: registers stay bounded for wide rows), ALL of a row's inputs
+// (dy, x, dres_in, mean, rstd) are requested one row ahead into raw registers, and the statistics pass / output pass
+// recompute xhat and g from those raw values instead of keeping them.
+template <typename T> struct Raw4;
+template <> struct Raw4<float> {
+  typedef float4 type;
+  static __device__ __forceinline__ type ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ float4 f(type v) { return v; }
+};
+template <> struct Raw4<__nv_bfloat16> {
+  typedef uint2 type;
+  static __device__ __forceinline__ type ld(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ float4 f(type v) {
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
+template <int NV, int WPR, typename TDY, typename TX>
+__global__ void __launch_bounds__(kLnWarps * 32, 3) add_ln_bwd_pipe_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                                        const float* __restrict__ mean,
+                                                                        const float* __restrict__ rstd,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ dres_in,
+                                                                        float* __restrict__ dx_f32,
+                                                                        __nv_bfloat16* __restrict__ dx_lp,
+                                                                        float* __restrict__ ws, int64_t M) {
+  constexpr int C = 128 * NV * WPR, kTeams = kLnWarps / WPR, kPart = 128 * NV;  // columns per warp
+  __shared__ float sred[kLnWarps][2][kPart];
+  __shared__ float2 sx[2][kLnWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / WPR, part = warp % WPR;
+  const int col0 = part * kPart + lane * 4;  // + 128 k
+  typedef typename Raw4<TDY>::type RD;
+  typedef typename Raw4<TX>::type RX;
+  float4 gm[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    gm[k] = *reinterpret_cast<const float4*>(gamma + col0 + 128 * k);
+    dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t stride = (int64_t)gridDim.x * kTeams;
+  int64_t row = (int64_t)blockIdx.x * kTeams + team;
+  RD d_n[NV];
+  RX x_n[NV];
+  float4 r_n[NV];
+  float mu_n = 0.f, rs_n = 0.f;
+  auto fetch = [&](int64_t r) {
+    const size_t base = (size_t)r * C + col0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      d_n[k] = Raw4<TDY>::ld(dy + base + 128 * k);
+      x_n[k] = Raw4<TX>::ld(x + base + 128 * k);
+      if (dres_in) r_n[k] = *reinterpret_cast<const float4*>(dres_in + base + 128 * k);
+    }
+    mu_n = mean[r];
+    rs_n = rstd[r];
+  };
+  if (row < M) fetch(row);
+  int it = 0;
+  for (; row < M; row += stride, ++it) {
+    RD d_c[NV];
+    RX x_c[NV];
+    float4 r_c[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { d_c[k] = d_n[k]; x_c[k] = x_n[k]; r_c[k] = r_n[k]; }
+    const float mu = mu_n, rs = rs_n;
+    if (row + stride < M) fetch(row + stride);  // next row's requests are in flight while this one is reduced and stored
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 d = Raw4<TDY>::f(d_c[k]), xv = Raw4<TX>::f(x_c[k]);
+      const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      const float4 g = make_float4(d.x * gm[k].x, d.y * gm[k].y, d.z * gm[k].z, d.w * gm[k].w);
+      s1 += (g.x + g.y) + (g.z + g.w);
+      s2 += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+      dg[k].x += d.x * xh.x; dg[k].y += d.y * xh.y; dg[k].z += d.z * xh.z; dg[k].w += d.w * xh.w;
+      db[k].x += d.x; db[k].y += d.y; db[k].z += d.z; db[k].w += d.w;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (WPR > 1) {  // the row's other warps: two alternating slots, one named barrier per row and team
+      if (lane == 0) sx[it & 1][warp] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(WPR * 32) : "memory");
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) { const float2 v = sx[it & 1][team * WPR + w]; s1 += v.x; s2 += v.y; }
+    }
+    const float c1 = s1 * (1.f / (float)C), c2 = s2 * (1.f / (float)C);
+    const size_t base = (size_t)row * C + col0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 d = Raw4<TDY>::f(d_c[k]), xv = Raw4<TX>::f(x_c[k]);
+      float4 o;
+      o.x = rs * (d.x * gm[k].x - c1 - (xv.x - mu) * rs * c2);
+      o.y = rs * (d.y * gm[k].y - c1 - (xv.y - mu) * rs * c2);
+      o.z = rs * (d.z * gm[k].z - c1 - (xv.z - mu) * rs * c2);
+      o.w = rs * (d.w * gm[k].w - c1 - (xv.w - mu) * rs * c2);
+      if (dres_in) { o.x += r_c[k].x; o.y += r_c[k].y; o.z += r_c[k].z; o.w += r_c[k].w; }
+      if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + base + 128 * k) = o;
+      if (dx_lp) Vec4<__nv_bfloat16>::st(dx_lp + base + 128 * k, o);
+    }
+  }
+  // CTA-level reduction of the parameter-gradient partials: warps with the same `part` hold the same columns
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    *reinterpret_cast<float4*>(&sred[warp][0][lane * 4 + 128 * k]) = dg[k];
+    *reinterpret_cast<float4*>(&sred[warp][1][lane * 4 + 128 * k]) = db[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i % C, pp = c / kPart, cc = c % kPart;
+    float a = 0.f;
+#pragma unroll
+    for (int t = 0; t < kTeams; ++t) a += sred[t * WPR + pp][which][cc];
+    ws[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
 // 32 columns x 32 row-slices per CTA; fixed summation order (slice-strided partials, then slices 0..31)
 __global__ void __launch_bounds__(1024) ln_bwd_finish_kernel(const float* __restrict__ ws, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int nblocks, int C) {
@@ -246,6 +369,43 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* mean, const
   return oct_check_launch("oct_add_ln_bwd(finish)");
 }
 
+template <int NV, int WPR>
+static int launch_ln_bwd_pipe_t(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                                const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma,
+                                float* dbeta, float* ws, int64_t M, cudaStream_t st) {
+  constexpr int C = 128 * NV * WPR, kTeams = kLnWarps / WPR;
+  int64_t blocks = ceil_div64(M, kTeams);
+  const int64_t cap = (int64_t)oct_num_sms() * 3;  // ~150 registers per thread: three CTAs per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks > ln_bwd_blocks(M)) blocks = ln_bwd_blocks(M);  // the workspace is sized by oct_add_ln_bwd_ws_bytes
+#define LNP(TDY, TX)                                                                                                   \
+  add_ln_bwd_pipe_kernel<NV, WPR, TDY, TX><<<(unsigned)blocks, kLnWarps * 32, 0, st>>>(                                \
+      (const TDY*)dy, (const TX*)x, mean, rstd, gamma, dres_in, dx_f32, (__nv_bfloat16*)dx_lp, ws, M)
+  if (dy_dtype == OCT_BF16 && x_dtype == OCT_F32) LNP(__nv_bfloat16, float);
+  else if (dy_dtype == OCT_F32 && x_dtype == OCT_F32) LNP(float, float);
+  else if (dy_dtype == OCT_BF16 && x_dtype == OCT_BF16) LNP(__nv_bfloat16, __nv_bfloat16);
+  else LNP(float, __nv_bfloat16);
+#undef LNP
+  int rc = oct_check_launch("oct_add_ln_bwd(pipe)");
+  if (rc) return rc;
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div64(2 * C, 32), dim3(32, 32), 0, st>>>(ws, dgamma, dbeta, (int)blocks, C);
+  return oct_check_launch("oct_add_ln_bwd(finish)");
+}
+
+static int launch_ln_bwd_pipe(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                              const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma,
+                              float* dbeta, float* ws, int64_t M, int C, cudaStream_t st) {
+#define A dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, ws, M, st
+  switch (C) {
+    case 128: return launch_ln_bwd_pipe_t<1, 1>(A);
+    case 256: return launch_ln_bwd_pipe_t<2, 1>(A);
+    case 512: return launch_ln_bwd_pipe_t<4, 1>(A);
+    case 1024: return launch_ln_bwd_pipe_t<4, 2>(A);
+    default: return OCT_ERR_UNSUPPORTED;
+  }
+#undef A
+}
+
 template <typename TDY, typename TX, typename TLP>
 static int dispatch_ln_bwd_nv(int nv, const void* dy, const void* x, const float* mean, const float* rstd,
                               const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma,
@@ -280,6 +440,11 @@ extern "C" int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x
   const int nv = nv_for(C);
   // the low-precision copy is only ever bf16 (or absent); dy and x each f32|bf16
   OCT_REQUIRE(!dx_lp || dx_lp_dtype == OCT_BF16, "oct_add_ln_bwd: dx_lp must be bf16");
+  if (getenv("OCT_LN_NO_PIPE") == nullptr) {
+    const int rc = launch_ln_bwd_pipe(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta,
+                                      (float*)ws, M, (int)C, st);
+    if (rc != OCT_ERR_UNSUPPORTED) return rc;  // widths the pipelined kernel does not cover fall through
+  }
 #define A nv, dy, x, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, (float*)ws, M, (int)C, st
   if (dy_dtype == OCT_F32 && x_dtype == OCT_F32) return dispatch_ln_bwd_nv<float, float, __nv_bfloat16>(A);
   if (dy_dtype == OCT_BF16 && x_dtype == OCT_F32) return dispatch_ln_bwd_nv<__nv_bfloat16, float, __nv_bfloat16>(A);

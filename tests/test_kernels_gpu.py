@@ -165,6 +165,29 @@ def test_add_ln_fwd_bwd(C, hdtype, ydtype):
     assert rel(gd.grad, gr.grad) < 1e-4 and rel(bd.grad, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("C", [128, 256, 512, 1024])
+def test_add_ln_bwd_pipelined_many_rows(C):
+    """Several rows per warp team: exercises the one-row-ahead prefetch and the two-warps-per-row statistics exchange."""
+    M = 5003
+    g = torch.Generator().manual_seed(C + 1)
+    h = (torch.randn(M, C, generator=g) * 2 + 0.5).bfloat16()
+    res = torch.randn(M, C, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    hr, rr = h.float().clone().requires_grad_(True), res.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    r_ref = hr + rr
+    y_ref = F.layer_norm(r_ref, (C,), gr, br, 1e-6)
+    dy, dres = torch.randn(M, C, generator=g).bfloat16(), torch.randn(M, C, generator=g)
+    (y_ref * dy.float()).sum().backward(retain_graph=True)
+    r_ref.backward(dres)
+    hd, rd = h.to(DEV).requires_grad_(True), res.to(DEV).requires_grad_(True)
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y, r = ops.AddLNFn.apply(hd, rd, gd, bd, 1e-6, torch.bfloat16, True)
+    torch.autograd.backward([y, r], [dy.to(DEV), dres.to(DEV)])
+    assert rel(rd.grad, rr.grad) < 1e-4 and rel(hd.grad, hr.grad) < 6e-3
+    assert rel(gd.grad, gr.grad) < 1e-4 and rel(bd.grad, br.grad) < 1e-4
+
+
 def test_ln_only_final_norm_form():
     M, C = 50, 64
     h = torch.randn(M, C).bfloat16()
