@@ -195,9 +195,11 @@ def main_b200(args):
         else:
             model.zero_grad(set_to_none=True)
         loss, _, _ = model(v, mask_ratio=MASK)                  # noise drawn on device, like models...:350
-        loss.backward()
         if reducer is not None:
+            reducer.backward(loss)                              # seeded with 1/world: the all-reduce yields DDP's mean
             reducer.finish()
+        else:
+            loss.backward()
         loss_out.copy_(loss.detach())
 
     # eager warm-up (also: TMA maps / func attributes / reducer bucket discovery), launch count of one step

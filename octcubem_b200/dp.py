@@ -9,6 +9,10 @@ and divided by the world size.  Mechanics are B200-first rather than DDP's:
     view of the bucket (no second copy after the collective);
   * a bucket is all-reduced on a dedicated side stream the moment its last gradient lands — NCCL over NVLink 5 /
     NVSwitch runs underneath the remaining backward kernels; `finish()` joins the streams;
+  * `reducer.backward(loss)` seeds the backward pass with 1 / world, so the SUM all-reduce already yields DDP's mean and
+    no scaling pass over the 1.3 GB of gradients follows the collective (a power-of-two scale: bit-identical);
+  * the Linear / Mlp weight gradients — 99 % of the bytes — are written by the wgrad GEMM straight into their bucket
+    views (`ops.grad_sinks`), so the hook has nothing to copy;
   * parameters that take no part in the step (the two high-res patch-embed tensors on a 3D-only step, quirk Q13) are
     discovered on the first, non-overlapped, step and left out of the buckets.
 Works on CPU tensors with the gloo backend (used by the world_size-2 tests) — there the "side stream" is implicit.
@@ -49,7 +53,9 @@ class GradReducer:
         self._hooks = []
         self._order: List[str] = []   # order in which gradients became ready on the discovery step
         self._named = dict(model.named_parameters())
+        self._sink_keys: List[int] = []
         self._discovering = True
+        self._prescaled = False
         dev = next(model.parameters()).device
         self.device = dev
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
@@ -84,6 +90,24 @@ class GradReducer:
         for bi, b in enumerate(buckets):
             for pi, p in enumerate(b.params):
                 self._slot[id(p)] = (bi, pi)
+        self._register_sinks()
+
+    def _register_sinks(self):
+        """CUDA path: the autograd Functions in ops.py write weight / bias gradients directly into the bucket views."""
+        if self.device.type != "cuda":
+            return
+        from . import ops
+        for b in self.buckets:
+            for p, v in zip(b.params, b.views):
+                ops.grad_sinks[p.data_ptr()] = v
+                self._sink_keys.append(p.data_ptr())
+
+    def _clear_sinks(self):
+        if self._sink_keys:
+            from . import ops
+            for k in self._sink_keys:
+                ops.grad_sinks.pop(k, None)
+        self._sink_keys = []
 
     def bucket_layout(self):
         return [(b.names, b.numel) for b in (self.buckets or [])]
@@ -115,11 +139,18 @@ class GradReducer:
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg)
-                b.flat.mul_(1.0 / self.world)
+                if not self._prescaled:
+                    b.flat.mul_(1.0 / self.world)
         else:
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     # ------------------------------------------------------------------ step protocol
+    def backward(self, loss: torch.Tensor):
+        """loss.backward() with the gradient seeded at 1 / world: the summed gradients are DDP's averages as they leave the
+        collective.  Follow with finish() as usual."""
+        self._prescaled = self.world > 1
+        loss.backward(gradient=torch.full_like(loss, 1.0 / self.world) if self.world > 1 else None)
+
     def finish(self):
         """Call after loss.backward(): joins the communication stream; on the discovery step performs the (non-overlapped)
         reduction and builds the buckets for the following steps."""
@@ -137,10 +168,12 @@ class GradReducer:
             for b in self.buckets:
                 if b.work is not None:
                     b.work.wait()
-                    b.flat.mul_(1.0 / self.world)
+                    if not self._prescaled:
+                        b.flat.mul_(1.0 / self.world)
                     b.work = None
         for b in self.buckets:
             b.pending = len(b.params)
+        self._prescaled = False
 
     def zero_grad(self):
         """Keeps param.grad pointing into the buckets (so the next hooks need no copy when autograd accumulates in place)
@@ -153,9 +186,11 @@ class GradReducer:
                 p.grad = None
 
     def reset(self):
+        self._clear_sinks()
         self.buckets, self._slot, self._order, self._discovering = None, {}, [], True
 
     def remove(self):
+        self._clear_sinks()
         for h in self._hooks:
             h.remove()
         self._hooks = []

@@ -110,17 +110,31 @@ def gemm(layout, A, B, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, aux=Non
     return out
 
 
-def wgrad_bias(dy2, x2):
+# parameter storage pointer -> fp32 tensor that should receive that parameter's gradient (dp.GradReducer registers the views
+# of its flat all-reduce buckets here, so that weight gradients are produced in place instead of being copied there)
+grad_sinks = {}
+
+
+def _sink(ptr, shape):
+    """A FRESH alias of the registered sink (autograd's AccumulateGrad adopts a gradient without copying only when nobody
+    else holds a reference to the very tensor object it is handed)."""
+    v = grad_sinks.get(ptr)
+    return None if v is None else v.view(shape)
+
+
+def wgrad_bias(dy2, x2, dw=None, db=None):
     """(dW [n_out, k_in], db [n_out]) = (dy2^T x2, column sums of dy2), both fp32.  bf16 operands: ONE tcgen05 kernel
     (oct_gemm_wgrad_bias: the bias gradient rides on the wgrad GEMM as an extra MMA against a tile of ones); fp32 parity
-    mode: CUDA-core GEMM + the deterministic two-stage column sum."""
-    _chk(dy2, x2)
+    mode: CUDA-core GEMM + the deterministic two-stage column sum.  dw / db: optional destinations (see grad_sinks)."""
+    _chk(dy2, x2, dw, db)
     tokens, n_out = dy2.shape
     k_in = x2.shape[1]
     if dy2.dtype != torch.bfloat16:
-        return gemm(GEMM_TN, dy2, x2, n_out, k_in, tokens, torch.float32), colsum(dy2)
-    dw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy2.device)
-    db = torch.empty(n_out, dtype=torch.float32, device=dy2.device)
+        return gemm(GEMM_TN, dy2, x2, n_out, k_in, tokens, torch.float32, out=dw), colsum(dy2, out=db)
+    if dw is None:
+        dw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy2.device)
+    if db is None:
+        db = torch.empty(n_out, dtype=torch.float32, device=dy2.device)
     _call("oct_gemm_wgrad_bias", OCT_BF16, _p(dy2), _p(x2), _p(dw), _p(db), n_out, k_in, tokens, dy2.stride(0), x2.stride(0),
           dw.stride(0), 0, _stream())
     return dw, db
@@ -224,6 +238,7 @@ class LinearFn(torch.autograd.Function):
         y = gemm(GEMM_NT, x2, w, M, N, K, x.dtype, EPI_BIAS, bias=bias)
         ctx.save_for_backward(x2, w)
         ctx.xshape = x.shape
+        ctx.sinks = (weight.data_ptr(), tuple(weight.shape), bias.data_ptr(), tuple(bias.shape))
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -238,7 +253,8 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(GEMM_NN, dy2, w, M, K, N, x2.dtype).view(ctx.xshape)
         if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
-            dw, db = wgrad_bias(dy2, x2)
+            wp, ws_, bp, bs = ctx.sinks
+            dw, db = wgrad_bias(dy2, x2, _sink(wp, ws_), _sink(bp, bs))
         elif ctx.needs_input_grad[1]:
             dw = gemm(GEMM_TN, dy2, x2, N, K, M, torch.float32)
         elif ctx.needs_input_grad[2]:
@@ -262,6 +278,7 @@ class MlpFn(torch.autograd.Function):
         y = gemm(GEMM_NT, act, wb, M, wb.shape[0], hid, x.dtype, EPI_BIAS, bias=b2)
         ctx.save_for_backward(x2, wa, wb, pre, act)
         ctx.xshape = x.shape
+        ctx.sinks = tuple((t.data_ptr(), tuple(t.shape)) for t in (w1, b1, w2, b2))
         return y.view(*x.shape[:-1], wb.shape[0])
 
     @staticmethod
@@ -274,9 +291,10 @@ class MlpFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         M = x2.shape[0]
         dpre = gemm(GEMM_NN, dy2, wb, M, hid, out_dim, x2.dtype, EPI_DGELU, aux=pre)
-        dw2, db2 = wgrad_bias(dy2, act)
+        (w1s, b1s, w2s, b2s) = ctx.sinks
+        dw2, db2 = wgrad_bias(dy2, act, _sink(*w2s), _sink(*b2s))
         dx = gemm(GEMM_NN, dpre, wa, M, dim, hid, x2.dtype).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        dw1, db1 = wgrad_bias(dpre, x2)
+        dw1, db1 = wgrad_bias(dpre, x2, _sink(*w1s), _sink(*b1s))
         return dx, dw1, db1, dw2, db2, None, None
 
 

@@ -48,7 +48,10 @@ def _worker(rank, world, port, path):
         red.zero_grad()
         x, y = X[step].chunk(world)[rank], Y[step].chunk(world)[rank]
         loss = ((net(x) - y) ** 2).mean()          # LOCAL mean (Q12)
-        loss.backward()
+        if step == 1:
+            red.backward(loss)                     # seeded with 1/world: no scaling pass after the collective
+        else:
+            loss.backward()
         red.finish()
         out.append({k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
     if rank == 0:
