@@ -137,6 +137,9 @@ class GradReducer:
             return
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            from . import ops
+            if ops._wgrad_pending.get(self.device.index, False):  # weight gradients are produced on their own stream
+                self.stream.wait_stream(ops.wgrad_stream(self.device))
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg)
                 if not self._prescaled:

@@ -122,6 +122,59 @@ def _sink(ptr, shape):
     return None if v is None else v.view(shape)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# weight gradients on a side stream: in the backward pass only the dgrad chain is sequential; the wgrad GEMMs are leaves.
+# Launched on a second stream (a parallel branch of the captured CUDA graph) their CTAs fill the SMs that the chain's
+# kernels leave idle (the encoder's N = 1024 GEMMs occupy 104 of 148 SMs, LN backward is HBM-bound, ...).
+# ----------------------------------------------------------------------------------------------------------------
+import os as _os
+
+overlap_wgrad = _os.environ.get("OCT_WGRAD_STREAM", "1") != "0"
+_wgrad_streams = {}
+_wgrad_pending = {}
+
+
+def wgrad_stream(device):
+    st = _wgrad_streams.get(device.index)
+    if st is None:
+        st = _wgrad_streams[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _join_wgrad(device):
+    """End of the backward pass (autograd engine callback): everything after it sees the weight gradients."""
+    def cb():
+        if _wgrad_pending.pop(device.index, False):
+            torch.cuda.current_stream(device).wait_stream(wgrad_stream(device))
+    return cb
+
+
+def join_wgrad(device=None):
+    """Make the current stream wait for the weight gradients launched so far (used by dp.GradReducer before a bucket's
+    all-reduce; a no-op when nothing is pending)."""
+    for idx in list(_wgrad_pending):
+        if device is None or device.index == idx:
+            torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(_wgrad_streams[idx])
+
+
+def wgrad_bias_async(dy2, x2, dw=None, db=None):
+    """wgrad_bias on the side stream (inside a backward pass, bf16 path); falls back to the current stream otherwise."""
+    if not overlap_wgrad or dy2.dtype != torch.bfloat16:
+        return wgrad_bias(dy2, x2, dw, db)
+    dev = dy2.device
+    side, cur = wgrad_stream(dev), torch.cuda.current_stream(dev)
+    if not _wgrad_pending.get(dev.index, False):
+        _wgrad_pending[dev.index] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad(dev))
+    side.wait_stream(cur)  # dy2 / x2 are complete on the current stream
+    with torch.cuda.stream(side):
+        out = wgrad_bias(dy2, x2, dw, db)
+    # the operands were allocated on the current stream: the caching allocator must not recycle them under the side stream
+    dy2.record_stream(side)
+    x2.record_stream(side)
+    return out
+
+
 def wgrad_bias(dy2, x2, dw=None, db=None):
     """(dW [n_out, k_in], db [n_out]) = (dy2^T x2, column sums of dy2), both fp32.  bf16 operands: ONE tcgen05 kernel
     (oct_gemm_wgrad_bias: the bias gradient rides on the wgrad GEMM as an extra MMA against a tile of ones); fp32 parity
@@ -250,15 +303,15 @@ class LinearFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         M = x2.shape[0]
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = gemm(GEMM_NN, dy2, w, M, K, N, x2.dtype).view(ctx.xshape)
-        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:  # first: it forks onto the wgrad stream and overlaps the dgrad
             wp, ws_, bp, bs = ctx.sinks
-            dw, db = wgrad_bias(dy2, x2, _sink(wp, ws_), _sink(bp, bs))
+            dw, db = wgrad_bias_async(dy2, x2, _sink(wp, ws_), _sink(bp, bs))
         elif ctx.needs_input_grad[1]:
             dw = gemm(GEMM_TN, dy2, x2, N, K, M, torch.float32)
         elif ctx.needs_input_grad[2]:
             db = colsum(dy2)
+        if ctx.needs_input_grad[0]:
+            dx = gemm(GEMM_NN, dy2, w, M, K, N, x2.dtype).view(ctx.xshape)
         return dx, dw, db, None
 
 
@@ -290,11 +343,11 @@ class MlpFn(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         M = x2.shape[0]
-        dpre = gemm(GEMM_NN, dy2, wb, M, hid, out_dim, x2.dtype, EPI_DGELU, aux=pre)
         (w1s, b1s, w2s, b2s) = ctx.sinks
-        dw2, db2 = wgrad_bias(dy2, act, _sink(*w2s), _sink(*b2s))
+        dw2, db2 = wgrad_bias_async(dy2, act, _sink(*w2s), _sink(*b2s))  # forks onto the wgrad stream: overlaps the dgrad chain
+        dpre = gemm(GEMM_NN, dy2, wb, M, hid, out_dim, x2.dtype, EPI_DGELU, aux=pre)
+        dw1, db1 = wgrad_bias_async(dpre, x2, _sink(*w1s), _sink(*b1s))
         dx = gemm(GEMM_NN, dpre, wa, M, dim, hid, x2.dtype).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        dw1, db1 = wgrad_bias(dpre, x2, _sink(*w1s), _sink(*b1s))
         return dx, dw1, db1, dw2, db2, None, None
 
 
