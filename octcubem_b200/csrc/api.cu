@@ -1,5 +1,6 @@
 // Library-level entry points: version, thread-local error string, device query.
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 static thread_local char g_err[512] = "";
@@ -21,6 +22,12 @@ int oct_check_launch(const char* what) {
     return (int)e;
   }
   return OCT_OK;
+}
+
+bool oct_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("OCT_PDL"); on = (e && e[0] == '1') ? 1 : 0; }  // opt-in: see common.cuh
+  return on != 0;
 }
 
 int oct_num_sms() {

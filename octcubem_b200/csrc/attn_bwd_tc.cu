@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const AbParams p) {
   using C = AbCfg<HD>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -143,6 +144,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // setmaxnreg sits at the top of each role's branch: ptxas budgets the registers of a region by the setmaxnreg that
   // dominates it (after a common if / else it applies the smaller value to everything that follows).
@@ -428,6 +430,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 template <int HD>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                   float* __restrict__ delta, int64_t total, int S, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= total) return;
   const uint4* a = reinterpret_cast<const uint4*>(out + w * HD);
@@ -452,6 +456,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 template <int HD>
 __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, int S, int H,
                                        int Spad, float scale, int64_t total4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*S*H*HD/4
   if (i >= total4) return;
   const int c4 = (int)(i % (HD / 4));
@@ -491,9 +497,8 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * H * Spad * HD * sizeof(float), st);
   if (e != cudaSuccess) { oct_set_error("oct_attn_bwd(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
   const int64_t rows = B * S * H;
-  attn_delta_kernel<HD><<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>((const __nv_bfloat16*)out,
-                                                                              (const __nv_bfloat16*)dout, delta, rows,
-                                                                              (int)S, (int)H);
+  oct_launch(attn_delta_kernel<HD>, dim3((unsigned)ceil_div64(rows, 256)), dim3(256), 0, st, 1, (const __nv_bfloat16*)out,
+             (const __nv_bfloat16*)dout, delta, rows, (int)S, (int)H);
   rc = oct_check_launch("oct_attn_bwd(bf16,delta)");
   if (rc) return rc;
   static bool attr_done = false;
@@ -507,12 +512,12 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dqkv = (__nv_bfloat16*)dqkv;
   { const char* e = getenv("OCT_ATTN_BWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   dim3 grid((unsigned)ceil_div64(S, AB_T), (unsigned)H, (unsigned)B);
-  attn_bwd_tc_kernel<HD><<<grid, AB_THREADS, C::kSmem, st>>>(mq, md, p);
+  oct_launch(attn_bwd_tc_kernel<HD>, grid, dim3(AB_THREADS), (size_t)C::kSmem, st, 1, mq, md, p);
   rc = oct_check_launch("oct_attn_bwd(bf16)");
   if (rc) return rc;
   const int64_t total4 = B * S * H * (HD / 4);
-  attn_dq_convert_kernel<HD><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (int)S,
-                                                                                (int)H, (int)Spad, scale, total4);
+  oct_launch(attn_dq_convert_kernel<HD>, dim3((unsigned)ceil_div64(total4, 256)), dim3(256), 0, st, 1, (const float*)dq_acc,
+             (__nv_bfloat16*)dqkv, (int)S, (int)H, (int)Spad, scale, total4);
   return oct_check_launch("oct_attn_bwd(bf16,dq)");
 }
 

@@ -144,6 +144,7 @@ template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                     const AtParams p) {
   using C = AtCfg<HD>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -346,7 +348,10 @@ int launch_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int
   AtParams p;
   p.S = (int)S; p.H = (int)H; p.scale_log2e = scale * kLog2e; p.out = (__nv_bfloat16*)out; p.lse = lse;
   dim3 grid((unsigned)ceil_div64(S, AT_QT * AT_BM), (unsigned)H, (unsigned)B);
-  attn_fwd_tc_kernel<HD><<<grid, AT_THREADS, C::kSmem, st>>>(map, p);
+  {
+    cudaError_t e = oct_launch(attn_fwd_tc_kernel<HD>, grid, dim3(AT_THREADS), (size_t)C::kSmem, st, 1, map, p);
+    if (e != cudaSuccess) { oct_set_error("oct_attn_fwd(bf16): launch: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   return oct_check_launch("oct_attn_fwd(bf16)");
 }
 

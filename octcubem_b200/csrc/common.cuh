@@ -28,10 +28,42 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int oct_num_sms();  // cached SM count of the current device (148 on B200)
 
+// Programmatic dependent launch: a kernel launched through oct_launch() may become resident while the previous kernel of
+// the stream (or captured graph) is still draining; it runs its prologue (mbarrier init, TMEM allocation, tensor-map
+// prefetch) and blocks in pdl_wait() until that kernel has completed and its writes are visible.  Every kernel signals
+// pdl_launch_dependents() first thing, so the overlap window is the tail of the grid.  OFF by default (OCT_PDL=1 enables
+// the launch attribute; without it the device-side instructions are no-ops): measured on the training step it LOSES 3 %
+// (36.2 vs 35.0 ms) because the early-resident CTAs of the next kernel in the chain take the SMs that the side-stream
+// weight-gradient GEMMs (ops.wgrad_bias_async) would otherwise fill.
+bool oct_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t oct_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (oct_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                                               const GemmParams p) {
   using C = Cfg<BLOCK_N, kColsum, kPair>;
   static_assert(!kColsum || A_MN, "the bias-gradient MMA sums the MN-major A operand over K");
+  pdl_launch_dependents();
   static_assert(!kPair || BLOCK_N == 256, "pair mode: 256 x 256 output tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (kPair) tc::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands / outputs are touched only below
 
   auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
     const int per_group = kGroupM * num_n;
@@ -505,22 +507,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   const int unit_m = kPair ? 2 * BLOCK_M : BLOCK_M;
   const int num_tiles = ((p.M + unit_m - 1) / unit_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int num_work = num_tiles * p.splits;
-  if (!kPair) {
-    const int grid = num_work < oct_num_sms() ? num_work : oct_num_sms();
-    kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, td, tx, p);
-  } else {
-    const int pairs = oct_num_sms() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (num_work < pairs ? num_work : pairs));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = C::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, p);
-    if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): cluster launch: %s", cudaGetErrorString(e)); return (int)e; }
+  {
+    const int units = kPair ? oct_num_sms() / 2 : oct_num_sms();
+    const int grid = (num_work < units ? num_work : units) * (kPair ? 2 : 1);
+    cudaError_t e = oct_launch(kern, dim3(grid), dim3(kThreads), (size_t)C::kSmemBytes, st, kPair ? 2 : 1, ta, tb, td, tx, p);
+    if (e != cudaSuccess) { oct_set_error("oct_gemm(bf16): launch: %s", cudaGetErrorString(e)); return (int)e; }
   }
   return oct_check_launch("oct_gemm(bf16)");
 }

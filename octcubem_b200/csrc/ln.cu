@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const TH* __r
                                                                    float* __restrict__ mean_out,
                                                                    float* __restrict__ rstd_out, int64_t M, int C,
                                                                    float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * kLnWarps;
   const int C4 = C >> 2;
@@ -82,8 +84,8 @@ static int launch_ln_fwd(const void* h, const float* res_in, float* res_out, con
   int64_t blocks = ceil_div64(M, kLnWarps);
   const int64_t cap = (int64_t)oct_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  add_ln_fwd_kernel<NV, TH, TY><<<(unsigned)blocks, kLnWarps * 32, 0, st>>>((const TH*)h, res_in, res_out, gamma, beta,
-                                                                           (TY*)y, mean, rstd, M, C, eps);
+  oct_launch(add_ln_fwd_kernel<NV, TH, TY>, dim3((unsigned)blocks), dim3(kLnWarps * 32), 0, st, 1, (const TH*)h, res_in, res_out,
+             gamma, beta, (TY*)y, mean, rstd, M, C, eps);
   return oct_check_launch("oct_add_ln_fwd");
 }
 
@@ -231,6 +233,8 @@ __global__ void __launch_bounds__(kLnWarps * 32, 3) add_ln_bwd_pipe_kernel(const
                                                                         __nv_bfloat16* __restrict__ dx_lp,
                                                                         float* __restrict__ ws, int64_t M) {
   constexpr int C = 128 * NV * WPR, kTeams = kLnWarps / WPR, kPart = 128 * NV;  // columns per warp
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sred[kLnWarps][2][kPart];
   __shared__ float2 sx[2][kLnWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -326,6 +330,8 @@ __global__ void __launch_bounds__(kLnWarps * 32, 3) add_ln_bwd_pipe_kernel(const
 __global__ void __launch_bounds__(1024) ln_bwd_finish_kernel(const float* __restrict__ ws, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int nblocks, int C) {
   __shared__ float sm[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
   if (i < 2 * C)
@@ -379,8 +385,8 @@ static int launch_ln_bwd_pipe_t(const void* dy, int dy_dtype, const void* x, int
   if (blocks > cap) blocks = cap;
   if (blocks > ln_bwd_blocks(M)) blocks = ln_bwd_blocks(M);  // the workspace is sized by oct_add_ln_bwd_ws_bytes
 #define LNP(TDY, TX)                                                                                                   \
-  add_ln_bwd_pipe_kernel<NV, WPR, TDY, TX><<<(unsigned)blocks, kLnWarps * 32, 0, st>>>(                                \
-      (const TDY*)dy, (const TX*)x, mean, rstd, gamma, dres_in, dx_f32, (__nv_bfloat16*)dx_lp, ws, M)
+  oct_launch(add_ln_bwd_pipe_kernel<NV, WPR, TDY, TX>, dim3((unsigned)blocks), dim3(kLnWarps * 32), 0, st, 1,         \
+             (const TDY*)dy, (const TX*)x, mean, rstd, gamma, dres_in, dx_f32, (__nv_bfloat16*)dx_lp, ws, M)
   if (dy_dtype == OCT_BF16 && x_dtype == OCT_F32) LNP(__nv_bfloat16, float);
   else if (dy_dtype == OCT_F32 && x_dtype == OCT_F32) LNP(float, float);
   else if (dy_dtype == OCT_BF16 && x_dtype == OCT_BF16) LNP(__nv_bfloat16, __nv_bfloat16);
@@ -388,7 +394,8 @@ static int launch_ln_bwd_pipe_t(const void* dy, int dy_dtype, const void* x, int
 #undef LNP
   int rc = oct_check_launch("oct_add_ln_bwd(pipe)");
   if (rc) return rc;
-  ln_bwd_finish_kernel<<<(unsigned)ceil_div64(2 * C, 32), dim3(32, 32), 0, st>>>(ws, dgamma, dbeta, (int)blocks, C);
+  oct_launch(ln_bwd_finish_kernel, dim3((unsigned)ceil_div64(2 * C, 32)), dim3(32, 32), 0, st, 1, (const float*)ws, dgamma, dbeta,
+             (int)blocks, C);
   return oct_check_launch("oct_add_ln_bwd(finish)");
 }
 
@@ -499,6 +506,8 @@ extern "C" int oct_gelu_bwd(const void* dy, const void* x, void* dx, int dtype, 
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
     Vec4<__nv_bfloat16>::st(dst + i * 4, *reinterpret_cast<const float4*>(src + i * 4));
@@ -508,7 +517,8 @@ extern "C" int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_
   OCT_REQUIRE(src && dst, "oct_cast_f32_to_bf16: null pointer");
   OCT_REQUIRE(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "oct_cast_f32_to_bf16: misaligned");
   if (n == 0) return OCT_OK;
-  cast_f32_bf16_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  oct_launch(cast_f32_bf16_kernel, dim3(ew_blocks(n / 4 + 1)), dim3(256), 0, (cudaStream_t)stream, 1, src, (__nv_bfloat16*)dst,
+             (int64_t)n);
   return oct_check_launch("oct_cast_f32_to_bf16");
 }
 
