@@ -78,15 +78,20 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
       for (int i = 0; i < 32; ++i)
         if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf
   }
-  float mx0 = -INFINITY, mx1 = -INFINITY;
+  // eight independent 3-input max chains (8 deep) instead of two (32 deep): the row maximum sits on the critical path of
+  // every tile (nothing else of this warp can issue until it is known), so its latency, not its instruction count, matters
+  float mx[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      mx0 = max3(mx0, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
-      mx1 = max3(mx1, __uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3]));
+    for (int i = 0; i < 32; i += 16) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        mx[q] = max3(mx[q], __uint_as_float(sr[c][i + 2 * q]), __uint_as_float(sr[c][i + 2 * q + 1]));
     }
-  const float m_tile = fmaxf(mx0, mx1) * scale_log2e;
+  const float m_tile = fmaxf(max3(mx[0], mx[1], mx[2]), fmaxf(max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * scale_log2e;
   const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? m_tile : m;
