@@ -415,8 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float2 pre = unpack_bf16x2(o[i]);
-              v[2 * i] = gelu_fast(pre.x);
-              v[2 * i + 1] = gelu_fast(pre.y);
+              tc::gelu_fast2(pre.x, pre.y, v[2 * i], v[2 * i + 1]);
             }
           } else if (p.epilogue == OCT_EPI_DGELU) {
             uint8_t* stg = stg_base + gg * kEpiStageBytes;
@@ -431,10 +430,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                            a3 = unpack_bf16x2(pre.w);
               const int i = 8 * q;
               uint4 out;
-              out.x = pack_bf16x2(v[i] * gelu_fast_grad(a0.x), v[i + 1] * gelu_fast_grad(a0.y));
-              out.y = pack_bf16x2(v[i + 2] * gelu_fast_grad(a1.x), v[i + 3] * gelu_fast_grad(a1.y));
-              out.z = pack_bf16x2(v[i + 4] * gelu_fast_grad(a2.x), v[i + 5] * gelu_fast_grad(a2.y));
-              out.w = pack_bf16x2(v[i + 6] * gelu_fast_grad(a3.x), v[i + 7] * gelu_fast_grad(a3.y));
+              float g0, g1;
+              tc::gelu_fast_grad2(a0.x, a0.y, v[i], v[i + 1], g0, g1);
+              out.x = pack_bf16x2(g0, g1);
+              tc::gelu_fast_grad2(a1.x, a1.y, v[i + 2], v[i + 3], g0, g1);
+              out.y = pack_bf16x2(g0, g1);
+              tc::gelu_fast_grad2(a2.x, a2.y, v[i + 4], v[i + 5], g0, g1);
+              out.z = pack_bf16x2(g0, g1);
+              tc::gelu_fast_grad2(a3.x, a3.y, v[i + 6], v[i + 7], g0, g1);
+              out.w = pack_bf16x2(g0, g1);
               *slot = out;  // in place: each thread owns its 128-byte row segment
             }
             tc::fence_proxy_async();

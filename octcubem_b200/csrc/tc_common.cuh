@@ -347,6 +347,46 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& p0, float& p1) {
   p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
 }
 
+// ---- GELU / dGELU of a PAIR on packed fp32x2 math (same A&S 7.1.26 erfc as gelu_fast in common.cuh, same constants) ----
+// The K = 512 GEMMs of the decoder MLP are bound by their epilogue (ncu: tensor pipe 30-35 % busy at fc1+GELU / fc2-dgrad+dGELU,
+// profiles/r1_gemm_ncu.md): ~30 scalar instructions per pair of outputs become 18-22.
+__device__ __forceinline__ uint64_t bcast2(float c) { return pack2(c, c); }
+__device__ __forceinline__ void gelu_parts2(float x0, float x1, uint64_t& nax, uint64_t& tail, uint64_t& e) {
+  nax = pack2(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));  // -|x|
+  const uint64_t u = fma2(nax, bcast2(-0.3275911f * 0.70710678118654752440f), bcast2(1.f));
+  float u0, u1, t0, t1;
+  unpack2(u, u0, u1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t t = pack2(t0, t1);
+  uint64_t poly = fma2(bcast2(0.5f * 1.061405429f), t, bcast2(0.5f * -1.453152027f));
+  poly = fma2(poly, t, bcast2(0.5f * 1.421413741f));
+  poly = fma2(poly, t, bcast2(0.5f * -0.284496736f));
+  poly = fma2(poly, t, bcast2(0.5f * 0.254829592f));
+  poly = mul2(poly, t);
+  const uint64_t x = pack2(x0, x1);
+  float a0, a1;
+  unpack2(mul2(mul2(x, x), bcast2(-0.72134752044448170368f)), a0, a1);  // -x^2/2 in log2 units
+  e = pack2(fast_exp2(a0), fast_exp2(a1));
+  tail = mul2(poly, e);  // Phi(-|x|)
+}
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& y0, float& y1) {
+  uint64_t nax, tail, e;
+  gelu_parts2(x0, x1, nax, tail, e);
+  unpack2(fma2(nax, tail, pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), y0, y1);  // relu(x) - |x| Phi(-|x|) = x Phi(x)
+}
+// dy * gelu'(x) for a pair: gelu'(x) = Phi(x) + x phi(x), Phi(x) = 1/2 + copysign(1/2 - Phi(-|x|), x)
+__device__ __forceinline__ void gelu_fast_grad2(float x0, float x1, float dy0, float dy1, float& g0, float& g1) {
+  uint64_t nax, tail, e;
+  gelu_parts2(x0, x1, nax, tail, e);
+  float h0, h1;
+  unpack2(fma2(tail, bcast2(-1.f), bcast2(0.5f)), h0, h1);  // 1/2 - tail >= 0
+  const uint64_t cdf = add2(bcast2(0.5f), pack2(__uint_as_float(__float_as_uint(h0) | (__float_as_uint(x0) & 0x80000000u)),
+                                               __uint_as_float(__float_as_uint(h1) | (__float_as_uint(x1) & 0x80000000u))));
+  const uint64_t d = fma2(mul2(pack2(x0, x1), bcast2(0.39894228040143267794f)), e, cdf);
+  unpack2(mul2(d, pack2(dy0, dy1)), g0, g1);
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----
