@@ -93,7 +93,8 @@ struct Cfg {
   static constexpr int kAccStages = kColsum ? 1 : 2;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages, or one + the colsum columns (power of two: 256 or 512)
   static constexpr int kColsumCol = BLOCK_N;     // TMEM column of the bias-gradient accumulator (kColsum)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + (kColsum ? kOnesBytes : 0) +
+  static constexpr int kBiasBytes = BLOCK_N * 4;  // the tile's bias values, staged once per tile by the epilogue warps
+  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + (kColsum ? kOnesBytes : 0) + kBiasBytes +
                                     1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
   uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // 2 column halves x 2 buffers x 16 KB, 1024-aligned
   uint8_t* smem_ones = smem_epi + 4 * kEpiStageBytes;      // kColsum: 2 KB of bf16 1.0, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + (kColsum ? kOnesBytes : 0));
+  float* smem_bias = reinterpret_cast<float*>(smem_ones + (kColsum ? kOnesBytes : 0));  // [2 column halves][BLOCK_N / 2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + C::kBiasBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -371,6 +373,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
         }
       }
+      const bool has_bias = (p.epilogue == OCT_EPI_BIAS || p.epilogue == OCT_EPI_BIAS_GELU);
+      float* sbias = smem_bias + colhalf * (BLOCK_N / 2);
+      if (has_bias) {
+        // this column half's bias values -> smem while the tile's MMAs are still running: the per-thread global loads of
+        // the same 64 values sat on the epilogue's critical path (long_scoreboard 25 %, profiles/r1_gemm_ncu.md).  The
+        // previous tile's readers are past the second bar.sync of their last staging call.
+        const int bc = n0 + colhalf * (BLOCK_N / 2) + tile_row;
+        if (tile_row < BLOCK_N / 2) sbias[tile_row] = (bc < p.N) ? __ldg(p.bias + bc) : 0.f;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
@@ -397,13 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           float v[64];
 #pragma unroll
           for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-          if (p.epilogue == OCT_EPI_BIAS || p.epilogue == OCT_EPI_BIAS_GELU) {
+          if (has_bias) {
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
-              if (nc + i < p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + i));
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-              }
+              const float4 b4 = *reinterpret_cast<const float4*>(sbias + gg * 64 + i);  // broadcast read
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
           }
           uint32_t o[32];
@@ -465,11 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tc::tmem_ld_x32(taddr + g * 32, o);
           tc::tmem_ld_wait();
           if (gg == kGroups - 1 || nc + 32 >= p.N) release_acc(acc);
-          if (p.epilogue == OCT_EPI_BIAS) {
+          if (has_bias) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              if (nc + i < p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + i));
+              {
+                const float4 b4 = *reinterpret_cast<const float4*>(sbias + gg * 32 + i);
                 o[i] = __float_as_uint(__uint_as_float(o[i]) + b4.x);
                 o[i + 1] = __float_as_uint(__uint_as_float(o[i + 1]) + b4.y);
                 o[i + 2] = __float_as_uint(__uint_as_float(o[i + 2]) + b4.z);
