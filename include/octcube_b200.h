@@ -168,6 +168,14 @@ int oct_mse_loss_bwd(const float* imgs, const int64_t* frame_idx, const void* pr
 /* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
 int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);
 
+/* ---- fused multi-tensor AdamW (replaces torch.optim._multi_tensor.AdamW, main_pretrain...:451-455, the GradScaler unscale
+ * before it and the next forward's bf16 weight casts) -----------------------------------------------------------------
+ * table [n_chunks][6] int64 on the device = {param f32*, grad f32*, exp_avg f32*, exp_avg_sq f32*, bf16 shadow* or 0, count}
+ * per chunk (count <= 16384; chunks never cross a tensor; pointers 16-byte aligned, shadow 8-byte).  One call = one parameter
+ * group (its lr / weight_decay); step counts from 1; grad_scale multiplies the gradient first (1/loss_scale, or 1). */
+int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int64_t step, float grad_scale, oct_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

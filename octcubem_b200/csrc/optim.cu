@@ -1,0 +1,75 @@
+// Fused multi-tensor AdamW step: replaces torch.optim._multi_tensor.AdamW at
+// Pre-training/main_pretrain_oph_joint_2d512_flash_attn.py:451-455 (betas 0.9 / 0.95, decoupled weight decay, no amsgrad)
+// plus the GradScaler unscale that precedes it (custom_util/misc.py:326-344) and the bf16 weight cast that autocast repeats at
+// the top of the next forward.  One launch per parameter group; HBM-bound: 16 B read + 12 B (+2 B shadow) written per parameter.
+//
+// Work is described by a device table of chunks (<= 16384 elements each, never crossing a tensor):
+//   row = { param f32*, grad f32*, exp_avg f32*, exp_avg_sq f32*, shadow bf16* (or 0), count }
+// Arithmetic order follows torch/optim/adamw.py (_multi_tensor): p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g g ;
+// denom = sqrt(v) / sqrt(bias_correction2) + eps ; p -= (lr / bias_correction1) * m / denom.
+#include "common.cuh"
+
+namespace {
+
+struct AdamWArgs {
+  float lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2_sqrt, grad_scale;
+};
+
+__device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, const AdamWArgs& a) {
+  g *= a.grad_scale;
+  p *= 1.f - a.lr * a.weight_decay;
+  m = m + (g - m) * (1.f - a.beta1);            // lerp(m, g, 1 - beta1), as torch._foreach_lerp_
+  v = v * a.beta2 + (g * g) * (1.f - a.beta2);  // mul_(beta2).addcmul_(g, g, 1 - beta2)
+  const float denom = sqrtf(v) / a.bias_corr2_sqrt + a.eps;
+  p -= (a.lr / a.bias_corr1) * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const int64_t* __restrict__ table, int n_chunks, AdamWArgs a) {
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int64_t* row = table + 6 * (int64_t)c;
+    float* p = reinterpret_cast<float*>(row[0]);
+    const float* g = reinterpret_cast<const float*>(row[1]);
+    float* m = reinterpret_cast<float*>(row[2]);
+    float* v = reinterpret_cast<float*>(row[3]);
+    __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(row[4]);
+    const int n = (int)row[5], n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      float4 p4 = *reinterpret_cast<float4*>(p + 4 * i);
+      const float4 g4 = *reinterpret_cast<const float4*>(g + 4 * i);
+      float4 m4 = *reinterpret_cast<float4*>(m + 4 * i), v4 = *reinterpret_cast<float4*>(v + 4 * i);
+      adamw1(p4.x, g4.x, m4.x, v4.x, a);
+      adamw1(p4.y, g4.y, m4.y, v4.y, a);
+      adamw1(p4.z, g4.z, m4.z, v4.z, a);
+      adamw1(p4.w, g4.w, m4.w, v4.w, a);
+      *reinterpret_cast<float4*>(p + 4 * i) = p4;
+      *reinterpret_cast<float4*>(m + 4 * i) = m4;
+      *reinterpret_cast<float4*>(v + 4 * i) = v4;
+      if (sh) Vec4<__nv_bfloat16>::st(sh + 4 * i, p4);
+    }
+    if (threadIdx.x < (n & 3)) {  // tail of a tensor whose size is not a multiple of 4
+      const int i = (n4 << 2) + threadIdx.x;
+      float pp = p[i], mm = m[i], vv = v[i];
+      adamw1(pp, g[i], mm, vv, a);
+      p[i] = pp; m[i] = mm; v[i] = vv;
+      if (sh) sh[i] = __float2bfloat16_rn(pp);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int64_t step, float grad_scale, oct_stream_t stream) {
+  OCT_REQUIRE(table || n_chunks == 0, "oct_adamw_step: null table");
+  OCT_REQUIRE(n_chunks >= 0 && n_chunks < (1 << 30), "oct_adamw_step: bad chunk count");
+  OCT_REQUIRE(step >= 1, "oct_adamw_step: step counts from 1");
+  OCT_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "oct_adamw_step: bad hyper-parameters");
+  if (n_chunks == 0) return OCT_OK;
+  AdamWArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  a.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  const int64_t cap = (int64_t)oct_num_sms() * 8;
+  adamw_multi_kernel<<<(unsigned)(n_chunks < cap ? n_chunks : cap), 256, 0, (cudaStream_t)stream>>>(table, (int)n_chunks, a);
+  return oct_check_launch("oct_adamw_step");
+}

@@ -45,7 +45,7 @@ class _Shadows:
         ent = self._m.get(id(p))
         if ent is None or ent["buf"].device != p.device or ent["buf"].shape != p.shape or ent["ptr"] != p.data_ptr():
             ent = {"buf": torch.empty(p.shape, dtype=torch.bfloat16, device=p.device), "ver": None,
-                   "ptr": p.data_ptr(), "fresh": False}
+                   "ptr": p.data_ptr(), "fresh": False, "p": p}
             self._m[id(p)] = ent
         capturing = torch.cuda.is_current_stream_capturing()
         if ent["ver"] != p._version or (capturing and not ent["fresh"]):
@@ -57,6 +57,15 @@ class _Shadows:
     def begin_step(self):
         for ent in self._m.values():
             ent["fresh"] = False
+
+    def buffer_of(self, p):
+        ent = self._m.get(id(p))
+        return None if ent is None or ent["ptr"] != p.data_ptr() else ent["buf"]
+
+    def mark_current(self):
+        """The shadows were just rewritten from the masters by someone else (optim.FusedAdamW): skip the next re-cast."""
+        for ent in self._m.values():
+            ent["ver"] = ent["p"]._version
 
 
 class _Ctx:
@@ -419,6 +428,16 @@ class MaskedAutoencoderViT(nn.Module):
         pred_full = self._decoder_tokens(latent, ids_restore, high_res)
         loss = self._loss(imgs, pred_full, 1, mask, frame_loss)
         return loss, pred_full[:, 1:, :], mask
+
+    # ------------------------------------------------------------------ optimizer hand-shake (optim.FusedAdamW)
+    def shadow_of(self, p):
+        """bf16 shadow buffer of a GEMM weight (None for parameters that have none, or before the first forward): pass
+        `shadows=model.shadow_of` to optim.FusedAdamW so that the update kernel also writes the bf16 copies, then call
+        `model.shadows_current()` after `optimizer.step()` — the next forward launches no weight casts."""
+        return self._rt.shadows.buffer_of(p)
+
+    def shadows_current(self):
+        self._rt.shadows.mark_current()
 
     def forward_patch_embed(self, imgs):
         """models...:777-790 -> [N, T'*L, C]."""

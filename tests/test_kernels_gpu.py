@@ -345,3 +345,52 @@ def test_gemm_tc_from_fresh_thread():
     t.join()
     assert "err" not in box, box.get("err")
     assert rel(box["out"], a.double() @ b.double().t()) < 2e-6
+
+
+# ---------------------------------------------------------------- optimizer
+def test_fused_adamw_matches_torch():
+    """oct_adamw_step vs torch.optim.AdamW (the reference's optimizer, main_pretrain...:451-455) over 4 steps, two groups
+    (decay / no decay, misc.add_weight_decay), a changing learning rate, odd tensor sizes, and the bf16 shadow output."""
+    from octcubem_b200 import optim
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 129), torch.nn.LayerNorm(129), torch.nn.Linear(129, 20001)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(37, 129), torch.nn.LayerNorm(129), torch.nn.Linear(129, 20001)).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    groups = optim.add_weight_decay(net, 0.05)
+    assert len(groups[0]["params"]) == 4 and len(groups[1]["params"]) == 2 and groups[0]["weight_decay"] == 0.0
+    shadows = {id(p): torch.zeros(p.shape, dtype=torch.bfloat16, device=DEV) for p in net.parameters() if p.dim() == 2}
+    opt = optim.FusedAdamW(groups, lr=1e-3, betas=(0.9, 0.95), shadows=lambda p: shadows.get(id(p)))
+    ropt = torch.optim.AdamW(optim.add_weight_decay(ref, 0.05), lr=1e-3, betas=(0.9, 0.95))
+    for step in range(4):
+        lr = optim.adjust_learning_rate(opt, step * 0.5, 1e-3, 1e-5, 1, 3)
+        assert lr == optim.adjust_learning_rate(ropt, step * 0.5, 1e-3, 1e-5, 1, 3)
+        g = torch.Generator().manual_seed(step)
+        x = torch.randn(8, 37, generator=g).to(DEV)
+        for m, o in ((net, opt), (ref, ropt)):
+            m.zero_grad(set_to_none=True)
+            (m(x) ** 2).mean().backward()
+        v0 = net[0].weight._version
+        opt.step()
+        ropt.step()
+        assert net[0].weight._version > v0
+        for (k, p), (_, r) in zip(net.named_parameters(), ref.named_parameters()):
+            assert rel(p.detach(), r.detach()) < 1e-6, (step, k)
+    for p in net.parameters():
+        if p.dim() == 2:
+            assert torch.equal(shadows[id(p)], p.detach().bfloat16())
+
+
+def test_fused_adamw_grad_scale_and_errors():
+    from octcubem_b200 import optim
+    p = torch.nn.Parameter(torch.randn(1000, device=DEV))
+    q = torch.nn.Parameter(p.detach().clone())
+    g = torch.randn(1000, device=DEV)
+    p.grad, q.grad = g * 1024.0, g.clone()
+    a, b = optim.FusedAdamW([p], lr=1e-2), optim.FusedAdamW([q], lr=1e-2)
+    a.step(grad_scale=1.0 / 1024.0)   # GradScaler unscale folded into the update
+    b.step()
+    assert rel(p.detach(), q.detach()) < 1e-6
+    cpu = torch.nn.Parameter(torch.randn(4))
+    cpu.grad = torch.randn(4)
+    with pytest.raises(RuntimeError):
+        optim.FusedAdamW([cpu]).step()
