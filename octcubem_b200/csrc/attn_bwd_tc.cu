@@ -60,7 +60,7 @@ struct AbParams {
   float scale, scale_log2e;
   const float* lse;     // [B,H,S]
   const float* delta;   // [B,H,S]
-  float* dq_acc;        // [B,H,Spad,HD] fp32, zero-initialised, 16-byte chunks of each row XOR-swizzled
+  float* dq_acc;        // [B,H,Spad/128][lane quarter][HD/4 chunks][32 rows][4] fp32, zero-initialised (see the drain warps)
   __nv_bfloat16* dqkv;  // [B,S,3,H,HD]
   int dbg;              // OCT_ATTN_BWD_DBG=16: record a cycle trace of CTA (1,0,0) (diagnostics only)
 };
@@ -301,9 +301,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AB_REGS_SOFTMAX));
     const int quarter = warp & 3, colhalf = warp >> 2;
     const int row = quarter * 32 + lane;  // kv row inside the tile == TMEM lane
-    const int tid = threadIdx.x;          // 0..255
     const bool kv_ok = (n0 + row) < p.S;
-    const bool partial_kv = (n0 + AB_T) > p.S;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const size_t bh = (size_t)b * p.H + h;
     // The eight warps never synchronise with each other (only through p_ready -> the MMA issuer): each warp stages the
