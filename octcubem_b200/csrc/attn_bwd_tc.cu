@@ -385,7 +385,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       AB_TRACE(9);
     }
 #if OCT_AB_TRACE
-    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
+    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
       for (int i = 0; i < 8; ++i)
         for (int k = 0; k < 14; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
     }
