@@ -172,9 +172,16 @@ int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t st
  * before it and the next forward's bf16 weight casts) -----------------------------------------------------------------
  * table [n_chunks][6] int64 on the device = {param f32*, grad f32*, exp_avg f32*, exp_avg_sq f32*, bf16 shadow* or 0, count}
  * per chunk (count <= 16384; chunks never cross a tensor; pointers 16-byte aligned, shadow 8-byte).  One call = one parameter
- * group (its lr / weight_decay); step counts from 1; grad_scale multiplies the gradient first (1/loss_scale, or 1). */
+ * group (its lr / weight_decay); step counts from 1; the gradient is first multiplied by grad_scale (1/loss_scale, or 1) and,
+ * if grad_scale_dev is not NULL, by that device scalar (the clip coefficient oct_grad_norm leaves in out[1]). */
 int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   int64_t step, float grad_scale, oct_stream_t stream);
+                   int64_t step, float grad_scale, const float* grad_scale_dev, oct_stream_t stream);
+
+/* global L2 norm of the gradients in `table` (same rows as oct_adamw_step; several groups = several tables concatenated by the
+ * caller) — misc.py:356-373: out[0] = grad_scale * ||g||_2 ; out[1] = max_norm > 0 ? min(1, max_norm / (out[0] + 1e-6)) : 1.
+ * partial: n_chunks floats of workspace; deterministic two-stage sum; nothing is copied to the host. */
+int oct_grad_norm(const int64_t* table, int64_t n_chunks, float grad_scale, float max_norm, float* partial, float* out,
+                  oct_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ namespace {
 
 struct AdamWArgs {
   float lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2_sqrt, grad_scale;
+  const float* grad_scale_dev;  // optional device scalar multiplied into grad_scale (the clip coefficient of oct_grad_norm)
 };
 
 __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, const AdamWArgs& a) {
@@ -25,6 +26,7 @@ __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, co
 }
 
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const int64_t* __restrict__ table, int n_chunks, AdamWArgs a) {
+  if (a.grad_scale_dev) a.grad_scale *= __ldg(a.grad_scale_dev);
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int64_t* row = table + 6 * (int64_t)c;
     float* p = reinterpret_cast<float*>(row[0]);
@@ -56,10 +58,59 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const int64_t* __restr
   }
 }
 
+// ---- global gradient norm + clip coefficient (custom_util/misc.py:356-373 get_grad_norm_ / clip_grad_norm_) ----------
+// partial[c] = sum of squares of chunk c (fixed order inside the chunk); one block then adds the partials in order:
+// out[0] = grad_scale * sqrt(sum), out[1] = max_norm > 0 ? min(1, max_norm / (out[0] + 1e-6)) : 1  (torch's clip coefficient)
+__global__ void __launch_bounds__(256) grad_sqnorm_partial_kernel(const int64_t* __restrict__ table, int n_chunks,
+                                                                  float* __restrict__ partial) {
+  __shared__ float sm[8];
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const float* g = reinterpret_cast<const float*>(table[6 * (int64_t)c + 1]);
+    const int n = (int)table[6 * (int64_t)c + 5], n4 = n >> 2;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 v = *reinterpret_cast<const float4*>(g + 4 * i);
+      acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    if (threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; acc += v * v; }
+    const float t = block_sum<8>(acc, sm);
+    if (threadIdx.x == 0) partial[c] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* __restrict__ partial, int n_chunks, float grad_scale,
+                                                                float max_norm, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_chunks; i += 1024) acc += partial[i];
+  const float t = block_sum<32>(acc, sm);
+  if (threadIdx.x == 0) {
+    const float norm = grad_scale * sqrtf(t);
+    out[0] = norm;
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+  }
+}
+
 }  // namespace
 
+extern "C" int oct_grad_norm(const int64_t* table, int64_t n_chunks, float grad_scale, float max_norm, float* partial,
+                             float* out, oct_stream_t stream) {
+  OCT_REQUIRE((table && partial) || n_chunks == 0, "oct_grad_norm: null table / workspace");
+  OCT_REQUIRE(out, "oct_grad_norm: null output");
+  OCT_REQUIRE(n_chunks >= 0 && n_chunks < (1 << 30), "oct_grad_norm: bad chunk count");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_chunks > 0) {
+    const int64_t cap = (int64_t)oct_num_sms() * 8;
+    grad_sqnorm_partial_kernel<<<(unsigned)(n_chunks < cap ? n_chunks : cap), 256, 0, st>>>(table, (int)n_chunks, partial);
+    int rc = oct_check_launch("oct_grad_norm(partial)");
+    if (rc) return rc;
+  }
+  grad_norm_finish_kernel<<<1, 1024, 0, st>>>(partial, (int)n_chunks, grad_scale, max_norm, out);
+  return oct_check_launch("oct_grad_norm(finish)");
+}
+
 extern "C" int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, float beta1, float beta2, float eps,
-                              float weight_decay, int64_t step, float grad_scale, oct_stream_t stream) {
+                              float weight_decay, int64_t step, float grad_scale, const float* grad_scale_dev,
+                              oct_stream_t stream) {
   OCT_REQUIRE(table || n_chunks == 0, "oct_adamw_step: null table");
   OCT_REQUIRE(n_chunks >= 0 && n_chunks < (1 << 30), "oct_adamw_step: bad chunk count");
   OCT_REQUIRE(step >= 1, "oct_adamw_step: step counts from 1");
@@ -67,6 +118,7 @@ extern "C" int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, 
   if (n_chunks == 0) return OCT_OK;
   AdamWArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  a.grad_scale_dev = grad_scale_dev;
   a.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   const int64_t cap = (int64_t)oct_num_sms() * 8;

@@ -53,6 +53,8 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._shadows = shadows
         self._tables = {}
+        self._norm_ws = None
+        self.grad_norm = None
 
     def _table(self, gi, group):
         live = [p for p in group["params"] if p.grad is not None]
@@ -85,12 +87,33 @@ class FusedAdamW(torch.optim.Optimizer):
         return ent
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0):
+    def step(self, closure=None, grad_scale: float = 1.0, max_grad_norm=None):
+        """grad_scale: multiplied into every gradient first (1 / loss_scale of a GradScaler).  max_grad_norm: clip the global
+        gradient norm like torch.nn.utils.clip_grad_norm_ (misc.py:326-344); the norm is computed on the device, left in
+        `self.grad_norm` (a 0-d CUDA tensor, as the reference's NativeScaler returns it) and never read by the host."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        clip_ptr = None
+        if max_grad_norm is not None:
+            tabs = [self._table(gi, g) for gi, g in enumerate(self.param_groups) if g["params"]]
+            tabs = [t for t in tabs if t[2] > 0]
+            if tabs:
+                key = tuple(t[1].data_ptr() for t in tabs)
+                if self._norm_ws is None or self._norm_ws[0] != key:
+                    allt = torch.cat([t[1] for t in tabs], 0)
+                    self._norm_ws = (key, allt, torch.empty(allt.shape[0], dtype=torch.float32, device=allt.device),
+                                     torch.empty(2, dtype=torch.float32, device=allt.device))
+                _, allt, partial, out = self._norm_ws
+                rc = lib.oct_grad_norm(ctypes.c_void_p(allt.data_ptr()), allt.shape[0], float(grad_scale), float(max_grad_norm),
+                                       ctypes.c_void_p(partial.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                       ctypes.c_void_p(torch.cuda.current_stream(allt.device).cuda_stream))
+                if rc != 0:
+                    raise RuntimeError(f"oct_grad_norm failed (code {rc}): {_lib.last_error()}")
+                self.grad_norm = out[0]
+                clip_ptr = ctypes.c_void_p(out[1:].data_ptr())
         for gi, group in enumerate(self.param_groups):
             if not group["params"]:
                 continue
@@ -104,7 +127,7 @@ class FusedAdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             dev = group["params"][0].device
             rc = lib.oct_adamw_step(ctypes.c_void_p(table.data_ptr()), n, float(group["lr"]), float(b1), float(b2),
-                                    float(group["eps"]), float(group["weight_decay"]), step, float(grad_scale),
+                                    float(group["eps"]), float(group["weight_decay"]), step, float(grad_scale), clip_ptr,
                                     ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             if rc != 0:
                 raise RuntimeError(f"oct_adamw_step failed (code {rc}): {_lib.last_error()}")

@@ -394,3 +394,25 @@ def test_fused_adamw_grad_scale_and_errors():
     cpu.grad = torch.randn(4)
     with pytest.raises(RuntimeError):
         optim.FusedAdamW([cpu]).step()
+
+
+def test_fused_adamw_clip_grad_norm():
+    """Device-side global norm + clip coefficient (oct_grad_norm) folded into the update, vs clip_grad_norm_ + AdamW."""
+    from octcubem_b200 import optim
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(33, 257), torch.nn.Linear(257, 9)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(33, 257), torch.nn.Linear(257, 9)).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    opt = optim.FusedAdamW(optim.add_weight_decay(net, 0.05), lr=1e-3, betas=(0.9, 0.95))
+    ropt = torch.optim.AdamW(optim.add_weight_decay(ref, 0.05), lr=1e-3, betas=(0.9, 0.95))
+    for step, max_norm in enumerate((0.05, 1e6, 0.3)):   # clipping, not clipping, clipping
+        x = torch.randn(16, 33, generator=torch.Generator().manual_seed(step)).to(DEV)
+        for m in (net, ref):
+            m.zero_grad(set_to_none=True)
+            (m(x) ** 2).mean().backward()
+        want = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm)
+        opt.step(max_grad_norm=max_norm)
+        ropt.step()
+        assert abs(float(opt.grad_norm) - float(want)) < 1e-5 * float(want)
+        for (k, p), (_, r) in zip(net.named_parameters(), ref.named_parameters()):
+            assert rel(p.detach(), r.detach()) < 2e-6, (step, k)
