@@ -56,6 +56,7 @@ class GradReducer:
         self._sink_keys: List[int] = []
         self._discovering = True
         self._prescaled = False
+        self._stream_used = False
         dev = next(model.parameters()).device
         self.device = dev
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
@@ -136,6 +137,7 @@ class GradReducer:
         if self.world == 1:
             return
         if self.stream is not None:
+            self._stream_used = True
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
             from . import ops
             if ops._wgrad_pending.get(self.device.index, False):  # weight gradients are produced on their own stream
@@ -166,7 +168,9 @@ class GradReducer:
                     p.grad = v
                 self._launch(b)
         if self.stream is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            if self._stream_used:  # (a wait on a stream that took no part in a CUDA-graph capture would invalidate it)
+                torch.cuda.current_stream(self.device).wait_stream(self.stream)
+                self._stream_used = False
         else:
             for b in self.buckets:
                 if b.work is not None:
