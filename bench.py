@@ -179,7 +179,8 @@ def main_b200(args):
     if world > 1:  # same weights on every rank (DDP broadcasts rank 0's at construction)
         for p in model.parameters():
             dist.broadcast(p.data, 0)
-    reducer = GradReducer(model) if world > 1 else None
+    bucket_mb = float(os.environ.get("OCT_BUCKET_MB", "32"))  # experiment knob; 32 MB is the measured default
+    reducer = GradReducer(model, bucket_mb=bucket_mb) if world > 1 else None
     L = (FRAMES // 3) * (IMG // 16) ** 2
 
     g = torch.Generator().manual_seed(100 + rank)
