@@ -82,6 +82,30 @@ def test_high_res_2d_branch_vs_oracle():
         assert rel(got[k], ref_g[k]) < FP32_TOL, k
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_joint_3d_plus_2d_step_vs_oracle(precision, tol):
+    """The joint recipe of engine_pretrain.py:117-149 (cfg-4): a 3D forward and a high-res 2D forward through the same module,
+    `loss = loss + loss_2d`, ONE backward.  Gradients must equal the sum of the two oracle steps, and — unlike either
+    single-branch step (quirk Q13) — every parameter receives one."""
+    sd, vol3, noise3 = toy_inputs()
+    vol2 = O.synthetic_volume(2, 3, 128, 128, seed=3, zero_pad_frames=0)
+    noise2 = O.synthetic_noise(2, 64, seed=6)
+    (ref3, g3) = O.forward_backward(TOY, sd, vol3, 0.9, noise3, frame_loss=True)
+    (ref2, g2) = O.forward_backward(TOY, sd, vol2, 0.75, noise2)
+    want = {k: g3.get(k, 0) + g2.get(k, 0) for k in set(g3) | set(g2)}
+    m = build(TOY, sd, precision)
+    (loss3, _fl), _, mask3 = m(vol3.to(DEV), mask_ratio=0.9, frame_loss=True, noise=noise3.to(DEV))
+    loss2, _, mask2 = m(vol2.to(DEV), mask_ratio=0.75, noise=noise2.to(DEV))
+    (loss3 + loss2).backward()
+    assert torch.equal(mask3.cpu(), ref3[2]) and torch.equal(mask2.cpu(), ref2[2])
+    ref_total = float(ref3[0][0]) + float(ref2[0])
+    assert abs(float(loss3 + loss2) - ref_total) < tol * abs(ref_total)
+    got = {k: p.grad for k, p in m.named_parameters()}
+    assert all(v is not None for v in got.values()) and set(got) == set(want)
+    for k in got:
+        assert rel(got[k], want[k]) < (tol if precision == "fp32" else 5e-2), k   # per-tensor bound of the toy-step test
+
+
 def test_module_surface_and_methods():
     sd, vol, noise = toy_inputs()
     m = build(TOY, sd, "fp32")
