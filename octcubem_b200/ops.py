@@ -150,10 +150,10 @@ def _join_wgrad(device):
 
 
 def join_wgrad(device=None):
-    """Make the current stream wait for the weight gradients launched so far (used by dp.GradReducer before a bucket's
-    all-reduce; a no-op when nothing is pending)."""
+    """Make the current stream wait for the weight gradients launched so far (a no-op when nothing is pending).  The
+    autograd-engine callback does this at the end of every backward pass; optim.FusedAdamW calls it defensively."""
     for idx in list(_wgrad_pending):
-        if device is None or device.index == idx:
+        if (device is None or device.index == idx) and _wgrad_pending.pop(idx, False):
             torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(_wgrad_streams[idx])
 
 
@@ -163,9 +163,10 @@ def wgrad_bias_async(dy2, x2, dw=None, db=None):
         return wgrad_bias(dy2, x2, dw, db)
     dev = dy2.device
     side, cur = wgrad_stream(dev), torch.cuda.current_stream(dev)
-    if not _wgrad_pending.get(dev.index, False):
-        _wgrad_pending[dev.index] = True
-        torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad(dev))
+    # one join callback per call (the first to run does the work): a backward pass that died half-way leaves the flag set,
+    # and the next pass must still be joined
+    _wgrad_pending[dev.index] = True
+    torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad(dev))
     side.wait_stream(cur)  # dy2 / x2 are complete on the current stream
     with torch.cuda.stream(side):
         out = wgrad_bias(dy2, x2, dw, db)

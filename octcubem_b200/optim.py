@@ -96,6 +96,8 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        from . import ops
+        ops.join_wgrad()  # weight gradients are produced on a side stream (normally already joined at the end of backward)
         clip_ptr = None
         if max_grad_norm is not None:
             tabs = [self._table(gi, g) for gi, g in enumerate(self.param_groups) if g["params"]]
