@@ -297,6 +297,15 @@ def main_b200(args):
     # roofline of the dominant kernel, timed alone at its in-step shape (CUDA events on the launching stream)
     roof = dominant_kernel_roofline(ops, dev, pk)
 
+    # the north star's encoder target: forward + backward of forward_encoder alone (patch-embed, masking, 24 ViT-L blocks
+    # at S = 410, final norm), as one CUDA graph, against the tensor-pipe peak
+    enc = None
+    if world == 1:
+        try:
+            enc = encoder_step(model, vol, pk, timed, args.steps)
+        except Exception as e:  # noqa
+            print(f"[bench] encoder-step timing skipped ({type(e).__name__}: {e})", file=sys.stderr)
+
     # optimizer step, informational (not on the hot path): our fused multi-tensor AdamW (one launch per
     # parameter group, also emits the bf16 weight shadows) next to torch's fused AdamW on the same parameters
     opt_ms = opt_torch_ms = None
@@ -335,6 +344,7 @@ def main_b200(args):
             "step_tflops_per_gpu": gf * BATCH / ms_step,
             "step_frac_of_bf16_sustained": gf * BATCH / ms_step / pk["bf16_sustained"],
             "roofline": roof,
+            "encoder_step": enc,
             "optimizer_ms": opt_ms,
             "optimizer_torch_fused_ms": opt_torch_ms,
             "loss": last_loss,
@@ -351,6 +361,46 @@ def main_b200(args):
     sys.stderr.flush()
     torch.cuda.synchronize()
     os._exit(0)
+
+
+# algorithmic GF per volume of the encoder blocks, forward (24 x (24 S dim^2 + 4 S^2 dim), S = keep + 1)
+ENC_GF_FWD = {48: 247.6 + 16.5, 60: 309.2 + 25.8}
+
+
+def encoder_step(model, vol, pk, timed, steps):
+    """forward_encoder + its backward (seeded with a fixed dlatent) on the bench batch, replayed as one CUDA graph."""
+    model.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        model._rt.shadows.begin_step()
+        lat, _, _ = model.forward_encoder(vol, MASK)
+    dlat = torch.randn(lat.shape, device=vol.device).to(lat.dtype) * 1e-3
+
+    def enc_step():
+        model.zero_grad(set_to_none=True)
+        model._rt.shadows.begin_step()
+        latent, _, _ = model.forward_encoder(vol, MASK)
+        latent.backward(dlat)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            enc_step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enc_step()
+    for _ in range(3):
+        graph.replay()
+    ms = timed(graph.replay, steps) / steps
+    model.zero_grad(set_to_none=True)
+    gf = 3.0 * ENC_GF_FWD[FRAMES] * BATCH                       # bwd = 2 x fwd
+    tf = gf / ms
+    return {"what": f"forward_encoder fwd+bwd, batch {BATCH}, S = {lat.shape[1] + 1}, 24 blocks (patch-embed / masking / LN kernels "
+                    "run inside the timed region; only the blocks' GEMM + attention FLOPs are counted)",
+            "ms": ms, "volumes_per_s": BATCH / (ms / 1e3), "tflops": tf, "frac_of_bf16_sustained": tf / pk["bf16_sustained"],
+            "frac_of_bf16_burst": tf / pk["bf16_burst"], "cuda_graph": True}
 
 
 def dominant_kernel_roofline(ops, dev, pk):

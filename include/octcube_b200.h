@@ -138,32 +138,42 @@ int oct_colsum(const void* x, int x_dtype, float* out, int64_t M, int64_t N, int
                size_t ws_bytes, oct_stream_t stream);
 
 /* ---- decoder un-shuffle + mask tokens + cls + separable pos add (models:515-573) --------------------------
- * out[b,0] = cls_row ; out[b,1+j] = (r<keep ? y[b,r] : mask_token) + pos_sp[j % G] + pos_tmp[j / G], r = ids_restore[b,j]
- * y [B,keep,D] f32|bf16 ; out [B,1+L,D] f32 (cls_row NULL -> no cls row, out [B,L,D]). */
+ * out[b,0] = cls_row ; out[b,1+j] = (r<keep ? y[b,y_row0+r] : mask_token) + pos_sp[j % G] + pos_tmp[j / G], r = ids_restore[b,j]
+ * y [B,y_row0+keep,D] f32|bf16 ; out [B,1+L,D] f32 (cls_row NULL -> no cls row, out [B,L,D]).
+ * y_row0 = 0: the 3D model (its encoder cls is dropped, models:491-493; the decoder cls is a parameter).
+ * y_row0 = 1: the 2D model (OCTCube/models_mae_flash_attn.py:299-312): row 0 of y is the sample's own cls token after
+ * decoder_embed, and out[b,0] = y[b,0] + cls_row (cls_row = decoder_pos_embed[0]). */
 int oct_unshuffle_fwd(const void* y, int y_dtype, const int64_t* ids_restore, const float* mask_token,
                       const float* pos_sp, const float* pos_tmp, const float* cls_row, float* out, int64_t B, int64_t L,
-                      int64_t keep, int64_t G, int64_t D, oct_stream_t stream);
-/* backward: dy [B,keep,D] ; d_mask_token [D], d_pos_sp [G,D], d_pos_tmp [L/G,D] (nullable), d_cls_row [D] (nullable)
- * are deterministic sums (overwritten).  ws >= oct_unshuffle_bwd_ws_bytes(B,L,G,D). */
+                      int64_t keep, int64_t G, int64_t D, int64_t y_row0, oct_stream_t stream);
+/* backward: dy [B,y_row0+keep,D] (row 0 = dout[b,0] when y_row0 = 1) ; d_mask_token [D], d_pos_sp [G,D], d_pos_tmp [L/G,D]
+ * (nullable), d_cls_row [D] (nullable) are deterministic sums (overwritten).  ws >= oct_unshuffle_bwd_ws_bytes(B,L,G,D). */
 size_t oct_unshuffle_bwd_ws_bytes(int64_t B, int64_t L, int64_t G, int64_t D);
 int oct_unshuffle_bwd(const float* dout, const int64_t* ids_restore, void* dy, int dy_dtype, float* d_mask_token,
                       float* d_pos_sp, float* d_pos_tmp, float* d_cls_row, void* ws, size_t ws_bytes, int64_t B,
-                      int64_t L, int64_t keep, int64_t G, int64_t D, int has_cls, oct_stream_t stream);
+                      int64_t L, int64_t keep, int64_t G, int64_t D, int has_cls, int64_t y_row0, oct_stream_t stream);
 
 /* ---- forward_loss (models:613-667): masked MSE on (optionally per-patch normalised) pixels ------------------
  * Reads the volume in place through patch indexing (no patchify copy).  imgs [B,1,T,H,W]; T_sel frames enter the loss
  * (T_sel == T, or frame_idx [T_sel] = linspace(0,T-1,pred_t_dim).long() of models:630-640); u = t_pred_patch_size.  pred [B, pred_rows, P] with the token j at
  * row (pred_row0 + j) (pred_row0 = 1 skips the cls row) ; mask [B,L] ; loss_tok [B,L] (workspace/out: per-patch mean
- * squared error, 0 where mask==0) ; loss [1] ; mask_sum [1] ; frame_losses [B,T'] ; sums are reduced in a fixed order. */
+ * squared error, 0 where mask==0) ; loss [1] ; mask_sum [1] ; frame_losses [B,T'] ; sums are reduced in a fixed order.
+ * flags: OCT_LOSS_NORM_PIX (1) per-patch normalised target (unbiased variance, eps 1e-6) ;
+ *        OCT_LOSS_CHANNEL_LAST (2) the 2D model's patch order 'nchpwq->nhwpqc' (OCTCube/models_mae_flash_attn.py:214-226):
+ *        imgs is [B,u,H,W] (u channels, T = T_sel = u) and element e of a patch is (kh, kw, c) with c fastest ;
+ *        OCT_LOSS_ALL_TOKENS (4) loss_tok is written for kept tokens too (the 2D model's return_frame_loss, :343-345). */
+#define OCT_LOSS_NORM_PIX 1
+#define OCT_LOSS_CHANNEL_LAST 2
+#define OCT_LOSS_ALL_TOKENS 4
 int oct_mse_loss_fwd(const float* imgs, const int64_t* frame_idx, const void* pred, int pred_dtype, const float* mask,
                      float* loss_tok, float* loss, float* mask_sum, float* frame_losses, int64_t B, int64_t T, int64_t T_sel,
-                     int64_t H, int64_t W, int64_t p, int64_t u, int64_t pred_rows, int64_t pred_row0, int norm_pix,
+                     int64_t H, int64_t W, int64_t p, int64_t u, int64_t pred_rows, int64_t pred_row0, int flags,
                      oct_stream_t stream);
 /* dpred [B,pred_rows,P] (rows < pred_row0 and kept tokens zero) = dloss · 2 (pred − target) · mask / (P · Σmask) */
 int oct_mse_loss_bwd(const float* imgs, const int64_t* frame_idx, const void* pred, int pred_dtype, const float* mask,
                      const float* mask_sum, const float* dloss, void* dpred, int dpred_dtype, int64_t B, int64_t T,
                      int64_t T_sel, int64_t H, int64_t W, int64_t p, int64_t u, int64_t pred_rows, int64_t pred_row0,
-                     int norm_pix, oct_stream_t stream);
+                     int flags, oct_stream_t stream);
 
 /* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
 int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);

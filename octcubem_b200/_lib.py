@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("OCT_LIB") or os.path.join(_HERE, "liboctcube_b200.so"
 OCT_F32, OCT_BF16, OCT_SIMT_BF16 = 0, 1, 2
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU = 0, 1, 2, 3
+LOSS_NORM_PIX, LOSS_CHANNEL_LAST, LOSS_ALL_TOKENS = 1, 2, 4
 
 P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 
@@ -42,9 +43,9 @@ SIGNATURES = {
     "oct_gelu_bwd": (I, [P, P, P, I, L, P]),
     "oct_colsum_ws_bytes": (Z, [L, L]),
     "oct_colsum": (I, [P, I, P, L, L, L, I, P, Z, P]),
-    "oct_unshuffle_fwd": (I, [P, I, P, P, P, P, P, P, L, L, L, L, L, P]),
+    "oct_unshuffle_fwd": (I, [P, I, P, P, P, P, P, P, L, L, L, L, L, L, P]),
     "oct_unshuffle_bwd_ws_bytes": (Z, [L, L, L, L]),
-    "oct_unshuffle_bwd": (I, [P, P, P, I, P, P, P, P, P, Z, L, L, L, L, L, I, P]),
+    "oct_unshuffle_bwd": (I, [P, P, P, I, P, P, P, P, P, Z, L, L, L, L, L, I, L, P]),
     "oct_mse_loss_fwd": (I, [P, P, P, I, P, P, P, P, P, L, L, L, L, L, L, L, L, L, I, P]),
     "oct_mse_loss_bwd": (I, [P, P, P, I, P, P, P, P, I, L, L, L, L, L, L, L, L, L, I, P]),
     "oct_cast_f32_to_bf16": (I, [P, P, L, P]),

@@ -5,9 +5,25 @@
 
 constexpr int kLossThreads = 192;  // 192 threads x float4 = 768 = 3*16*16 pixels in one pass
 
+constexpr int kLossNormPix = 1, kLossChannelLast = 2, kLossAllTokens = 4;  // OCT_LOSS_* of include/octcube_b200.h
+
 // loads element quad e4 of the target patch of token (b,t,h,w)
 __device__ __forceinline__ float4 load_target4(const float* __restrict__ imgs, const int64_t* __restrict__ frame_idx,
-                                               int b, int t, int h, int w, int e4, int T, int H, int W, int p, int u) {
+                                               int b, int t, int h, int w, int e4, int T, int H, int W, int p, int u,
+                                               bool chan_last) {
+  if (chan_last) {
+    // 2D model (OCTCube/models_mae_flash_attn.py:214-226, 'nchpwq->nhwpqc'): element e = (kh * p + kw) * u + c, the u
+    // channels are the "frames" of the [B,u,H,W] image; four consecutive elements straddle channels -> scalar loads
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e4 * 4 + i;
+      const int c = e % u, q = e / u;
+      const int kw = q % p, kh = q / p;
+      r[i] = imgs[(((size_t)b * T + (t * u + c)) * H + (h * p + kh)) * W + w * p + kw];
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+  }
   const int p4 = p >> 2;
   const int kw4 = e4 % p4, kh = (e4 / p4) % p, kt = e4 / (p4 * p);
   int f = t * u + kt;
@@ -20,8 +36,9 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
     const float* __restrict__ imgs, const int64_t* __restrict__ frame_idx, const TP* __restrict__ pred,
     const float* __restrict__ mask, float* __restrict__ loss_tok, const float* __restrict__ mask_sum,
     const float* __restrict__ dloss, TD* __restrict__ dpred, int T, int H, int W, int p, int u, int L, int pred_rows,
-    int pred_row0, int norm_pix) {
+    int pred_row0, int flags) {
   __shared__ float sred[32];
+  const bool norm_pix = flags & kLossNormPix, cl = flags & kLossChannelLast;
   const int b = blockIdx.y;
   const int P = u * p * p, P4 = P >> 2;
   int j;  // token index
@@ -36,7 +53,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
     }
   } else {
     j = blockIdx.x;
-    if (mask[(size_t)b * L + j] == 0.f) {
+    if (!(flags & kLossAllTokens) && mask[(size_t)b * L + j] == 0.f) {
       if (threadIdx.x == 0) loss_tok[(size_t)b * L + j] = 0.f;
       return;
     }
@@ -49,13 +66,13 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
   if (norm_pix) {  // models:644-647 — mean, UNBIASED variance, eps 1e-6
     float sum = 0.f;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 v = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u);
+      float4 v = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
       sum += (v.x + v.y) + (v.z + v.w);
     }
     mean = block_sum(sum, sred) / (float)P;
     float sq = 0.f;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 v = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u);
+      float4 v = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
       const float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
       sq += (a * a + c * c) + (d * d + e * e);
     }
@@ -66,7 +83,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
   if (!kBackward) {
     float acc = 0.f;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 tg = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u);
+      float4 tg = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
       const float4 pr = Vec4<TP>::ld(prow + e4 * 4);
       const float a = pr.x - (tg.x - mean) * inv_std, c = pr.y - (tg.y - mean) * inv_std;
       const float d = pr.z - (tg.z - mean) * inv_std, e = pr.w - (tg.w - mean) * inv_std;
@@ -78,7 +95,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
     const float coef = dloss[0] * 2.f / ((float)P * mask_sum[0]);
     TD* drow = dpred + ((size_t)b * pred_rows + pred_row0 + j) * P;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 tg = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u);
+      float4 tg = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
       const float4 pr = Vec4<TP>::ld(prow + e4 * 4);
       float4 o;
       o.x = coef * (pr.x - (tg.x - mean) * inv_std);
@@ -134,8 +151,9 @@ static int check_loss_args(int64_t B, int64_t T, int64_t T_sel, const int64_t* f
 extern "C" int oct_mse_loss_fwd(const float* imgs, const int64_t* frame_idx, const void* pred, int pred_dtype,
                                 const float* mask, float* loss_tok, float* loss, float* mask_sum, float* frame_losses,
                                 int64_t B, int64_t T, int64_t T_sel, int64_t H, int64_t W, int64_t p, int64_t u,
-                                int64_t pred_rows, int64_t pred_row0, int norm_pix, oct_stream_t stream) {
+                                int64_t pred_rows, int64_t pred_row0, int flags, oct_stream_t stream) {
   OCT_REQUIRE(imgs && pred && mask && loss_tok && loss && mask_sum && frame_losses, "oct_mse_loss_fwd: null pointer");
+  OCT_REQUIRE(!(flags & kLossChannelLast) || (!frame_idx && T == u), "oct_mse_loss_fwd: channel-last needs T == u, no frame_idx");
   int64_t L;
   int rc = check_loss_args(B, T, T_sel, frame_idx, H, W, p, u, pred_rows, pred_row0, &L, "oct_mse_loss_fwd");
   if (rc) return rc;
@@ -145,7 +163,7 @@ extern "C" int oct_mse_loss_fwd(const float* imgs, const int64_t* frame_idx, con
 #define LAUNCH(TP)                                                                                                   \
   mse_loss_token_kernel<TP, false, float><<<grid, kLossThreads, 0, st>>>(imgs, frame_idx, (const TP*)pred, mask,     \
       loss_tok, nullptr, nullptr, nullptr, (int)T, (int)H, (int)W, (int)p, (int)u, (int)L, (int)pred_rows,            \
-      (int)pred_row0, norm_pix)
+      (int)pred_row0, flags)
   if (pred_dtype == OCT_F32) LAUNCH(float);
   else if (pred_dtype == OCT_BF16) LAUNCH(__nv_bfloat16);
   else OCT_REQUIRE(false, "oct_mse_loss_fwd: bad dtype");
@@ -161,8 +179,9 @@ extern "C" int oct_mse_loss_fwd(const float* imgs, const int64_t* frame_idx, con
 extern "C" int oct_mse_loss_bwd(const float* imgs, const int64_t* frame_idx, const void* pred, int pred_dtype,
                                 const float* mask, const float* mask_sum, const float* dloss, void* dpred,
                                 int dpred_dtype, int64_t B, int64_t T, int64_t T_sel, int64_t H, int64_t W, int64_t p,
-                                int64_t u, int64_t pred_rows, int64_t pred_row0, int norm_pix, oct_stream_t stream) {
+                                int64_t u, int64_t pred_rows, int64_t pred_row0, int flags, oct_stream_t stream) {
   OCT_REQUIRE(imgs && pred && mask && mask_sum && dloss && dpred, "oct_mse_loss_bwd: null pointer");
+  OCT_REQUIRE(!(flags & kLossChannelLast) || (!frame_idx && T == u), "oct_mse_loss_bwd: channel-last needs T == u, no frame_idx");
   OCT_REQUIRE(pred_dtype == dpred_dtype, "oct_mse_loss_bwd: dpred dtype must equal pred dtype");
   int64_t L;
   int rc = check_loss_args(B, T, T_sel, frame_idx, H, W, p, u, pred_rows, pred_row0, &L, "oct_mse_loss_bwd");
@@ -173,7 +192,7 @@ extern "C" int oct_mse_loss_bwd(const float* imgs, const int64_t* frame_idx, con
 #define LAUNCH(TP)                                                                                                   \
   mse_loss_token_kernel<TP, true, TP><<<grid, kLossThreads, 0, st>>>(imgs, frame_idx, (const TP*)pred, mask, nullptr, \
       mask_sum, dloss, (TP*)dpred, (int)T, (int)H, (int)W, (int)p, (int)u, (int)L, (int)pred_rows, (int)pred_row0,    \
-      norm_pix)
+      flags)
   if (pred_dtype == OCT_F32) LAUNCH(float);
   else if (pred_dtype == OCT_BF16) LAUNCH(__nv_bfloat16);
   else OCT_REQUIRE(false, "oct_mse_loss_bwd: bad dtype");

@@ -308,18 +308,26 @@ template <typename TY>
 __global__ void unshuffle_fwd_kernel(const TY* __restrict__ y, const int64_t* __restrict__ ids_restore,
                                      const float* __restrict__ mask_token, const float* __restrict__ pos_sp,
                                      const float* __restrict__ pos_tmp, const float* __restrict__ cls_row,
-                                     float* __restrict__ out, int L, int keep, int G, int D, int has_cls) {
+                                     float* __restrict__ out, int L, int keep, int G, int D, int has_cls,
+                                     int y_row0) {
   const int r = blockIdx.x, b = blockIdx.y;
   float* o = out + ((size_t)b * (L + has_cls) + r) * D;
+  const TY* yb = y + (size_t)b * (keep + y_row0) * D;  // this sample's rows: [cls row (y_row0 == 1)] + keep token rows
   if (has_cls && r == 0) {
-    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)
-      *reinterpret_cast<float4*>(o + c) = *reinterpret_cast<const float4*>(cls_row + c);
+    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+      float4 v = *reinterpret_cast<const float4*>(cls_row + c);
+      if (y_row0) {  // per-sample cls token that went through decoder_embed (OCTCube/models_mae_flash_attn.py:301-309)
+        const float4 a = Vec4<TY>::ld(yb + c);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      *reinterpret_cast<float4*>(o + c) = v;
+    }
     return;
   }
   const int j = r - has_cls;
   const int src = (int)ids_restore[(size_t)b * L + j];
   const int t = j / G, s = j - t * G;
-  const TY* yr = y + ((size_t)b * keep + src) * D;
+  const TY* yr = yb + ((size_t)y_row0 + src) * D;
   for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
     float4 v = (src < keep) ? Vec4<TY>::ld(yr + c) : *reinterpret_cast<const float4*>(mask_token + c);
     float4 a = *reinterpret_cast<const float4*>(pos_sp + (size_t)s * D + c);
@@ -334,8 +342,9 @@ __global__ void unshuffle_fwd_kernel(const TY* __restrict__ y, const int64_t* __
 
 extern "C" int oct_unshuffle_fwd(const void* y, int y_dtype, const int64_t* ids_restore, const float* mask_token,
                                  const float* pos_sp, const float* pos_tmp, const float* cls_row, float* out, int64_t B,
-                                 int64_t L, int64_t keep, int64_t G, int64_t D, oct_stream_t stream) {
-  OCT_REQUIRE(ids_restore && mask_token && pos_sp && out && (y || keep == 0), "oct_unshuffle_fwd: null pointer");
+                                 int64_t L, int64_t keep, int64_t G, int64_t D, int64_t y_row0, oct_stream_t stream) {
+  OCT_REQUIRE(ids_restore && mask_token && pos_sp && out && (y || keep + y_row0 == 0), "oct_unshuffle_fwd: null pointer");
+  OCT_REQUIRE(y_row0 == 0 || (y_row0 == 1 && cls_row), "oct_unshuffle_fwd: y_row0 must be 0, or 1 together with cls_row");
   OCT_REQUIRE(D % 4 == 0 && G > 0 && L % G == 0, "oct_unshuffle_fwd: need D%%4==0 and L%%G==0");
   OCT_REQUIRE(pos_tmp || L == G, "oct_unshuffle_fwd: pos_tmp may be NULL only when T'==1");
   const int has_cls = cls_row ? 1 : 0;
@@ -344,25 +353,34 @@ extern "C" int oct_unshuffle_fwd(const void* y, int y_dtype, const int64_t* ids_
   const int threads = (int)((D / 4 < 256) ? ((D / 4 + 31) / 32 * 32) : 256);
   if (y_dtype == OCT_F32)
     unshuffle_fwd_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(
-        (const float*)y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row, out, (int)L, (int)keep, (int)G, (int)D, has_cls);
+        (const float*)y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row, out, (int)L, (int)keep, (int)G, (int)D, has_cls,
+        (int)y_row0);
   else if (y_dtype == OCT_BF16)
     unshuffle_fwd_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row, out, (int)L, (int)keep, (int)G, (int)D,
-        has_cls);
+        has_cls, (int)y_row0);
   else
     OCT_REQUIRE(false, "oct_unshuffle_fwd: bad dtype");
   return oct_check_launch("oct_unshuffle_fwd");
 }
 
-// backward 1: dy[b, r] = dout[b, 1 + j] where r = ids_restore[b, j] < keep (a permutation: every r written once)
+// backward 1: dy[b, y_row0 + r] = dout[b, 1 + j] where r = ids_restore[b, j] < keep (a permutation: every r written once);
+// with y_row0 == 1 the extra CTA j == L copies the cls row: dy[b, 0] = dout[b, 0]
 template <typename TD>
 __global__ void unshuffle_bwd_scatter_kernel(const float* __restrict__ dout, const int64_t* __restrict__ ids_restore,
-                                             TD* __restrict__ dy, int L, int keep, int D, int has_cls) {
+                                             TD* __restrict__ dy, int L, int keep, int D, int has_cls, int y_row0) {
   const int j = blockIdx.x, b = blockIdx.y;
+  TD* dyb = dy + (size_t)b * (keep + y_row0) * D;
+  if (j == L) {
+    const float* src = dout + (size_t)b * (L + has_cls) * D;
+    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)
+      Vec4<TD>::st(dyb + c, *reinterpret_cast<const float4*>(src + c));
+    return;
+  }
   const int r = (int)ids_restore[(size_t)b * L + j];
   if (r >= keep) return;
   const float* src = dout + ((size_t)b * (L + has_cls) + j + has_cls) * D;
-  TD* dst = dy + ((size_t)b * keep + r) * D;
+  TD* dst = dyb + ((size_t)y_row0 + r) * D;
   for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)
     Vec4<TD>::st(dst + c, *reinterpret_cast<const float4*>(src + c));
 }
@@ -434,8 +452,9 @@ extern "C" size_t oct_unshuffle_bwd_ws_bytes(int64_t B, int64_t L, int64_t G, in
 extern "C" int oct_unshuffle_bwd(const float* dout, const int64_t* ids_restore, void* dy, int dy_dtype,
                                  float* d_mask_token, float* d_pos_sp, float* d_pos_tmp, float* d_cls_row, void* ws,
                                  size_t ws_bytes, int64_t B, int64_t L, int64_t keep, int64_t G, int64_t D, int has_cls,
-                                 oct_stream_t stream) {
+                                 int64_t y_row0, oct_stream_t stream) {
   OCT_REQUIRE(dout && ids_restore && d_mask_token && d_pos_sp, "oct_unshuffle_bwd: null pointer");
+  OCT_REQUIRE(y_row0 == 0 || (y_row0 == 1 && has_cls && dy), "oct_unshuffle_bwd: y_row0 must be 0, or 1 together with has_cls and dy");
   OCT_REQUIRE(D % 4 == 0 && G > 0 && L % G == 0, "oct_unshuffle_bwd: need D%%4==0 and L%%G==0");
   OCT_REQUIRE((has_cls != 0) == (d_cls_row != nullptr), "oct_unshuffle_bwd: has_cls / d_cls_row mismatch");
   if (ws_bytes < oct_unshuffle_bwd_ws_bytes(B, L, G, D) || !ws) {
@@ -446,14 +465,14 @@ extern "C" int oct_unshuffle_bwd(const float* dout, const int64_t* ids_restore, 
   cudaStream_t st = (cudaStream_t)stream;
   const int Tp = (int)(L / G);
   const int threads = (int)((D / 4 < 256) ? ((D / 4 + 31) / 32 * 32) : 256);
-  if (dy && keep > 0) {
-    dim3 grid((unsigned)L, (unsigned)B);
+  if (dy && keep + y_row0 > 0) {
+    dim3 grid((unsigned)(L + y_row0), (unsigned)B);
     if (dy_dtype == OCT_F32)
       unshuffle_bwd_scatter_kernel<float><<<grid, threads, 0, st>>>(dout, ids_restore, (float*)dy, (int)L, (int)keep,
-                                                                    (int)D, has_cls);
+                                                                    (int)D, has_cls, (int)y_row0);
     else if (dy_dtype == OCT_BF16)
       unshuffle_bwd_scatter_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(dout, ids_restore, (__nv_bfloat16*)dy,
-                                                                           (int)L, (int)keep, (int)D, has_cls);
+                                                                           (int)L, (int)keep, (int)D, has_cls, (int)y_row0);
     else
       OCT_REQUIRE(false, "oct_unshuffle_bwd: bad dtype");
     int rc = oct_check_launch("oct_unshuffle_bwd(scatter)");

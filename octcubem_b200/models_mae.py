@@ -409,7 +409,7 @@ class MaskedAutoencoderViT(nn.Module):
             idx = torch.linspace(0, T - 1, self.pred_t_dim).long()
             if idx.numel() != T or not torch.equal(idx, torch.arange(T)):
                 frame_idx = idx.to(imgs.device)
-        loss, frame_losses = ops.MaskedMSELossFn.apply(imgs.contiguous().float(), pred_full, mask.contiguous(),
+        loss, frame_losses, _ = ops.MaskedMSELossFn.apply(imgs.contiguous().float(), pred_full, mask.contiguous(),
                                                        pe.patch_size[0], self.t_pred_patch_size, row0,
                                                        bool(self.norm_pix_loss), frame_idx)
         return (loss, frame_losses) if frame_loss else loss

@@ -488,30 +488,33 @@ class EmbedTokensFn(torch.autograd.Function):
 
 
 class UnshuffleFn(torch.autograd.Function):
-    """Decoder input assembly (models:515-573): mask tokens + un-shuffle by ids_restore + decoder cls + pos add."""
+    """Decoder input assembly (models:515-573): mask tokens + un-shuffle by ids_restore + decoder cls + pos add.
+    y_row0 = 1 is the 2D model's variant (OCTCube/models_mae_flash_attn.py:299-312): y [B, 1 + keep, D] carries the sample's
+    own cls token in row 0 and out[b, 0] = y[b, 0] + cls_row."""
 
     @staticmethod
-    def forward(ctx, y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row):
+    def forward(ctx, y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row, y_row0=0):
         _chk(y, ids_restore, mask_token, pos_sp, pos_tmp, cls_row)
-        B, keep, D = y.shape
+        B, D = y.shape[0], y.shape[2]
+        keep = y.shape[1] - y_row0
         L = ids_restore.shape[1]
         G = pos_sp.shape[0]
         has_cls = cls_row is not None
         out = torch.empty(B, L + (1 if has_cls else 0), D, dtype=torch.float32, device=y.device)
         _call("oct_unshuffle_fwd", _p(y), _dt(y), _p(ids_restore), _p(mask_token), _p(pos_sp), _p(pos_tmp), _p(cls_row), _p(out),
-              B, L, keep, G, D, _stream())
+              B, L, keep, G, D, y_row0, _stream())
         ctx.save_for_backward(ids_restore)
-        ctx.dims = (B, L, keep, G, D, y.dtype, pos_tmp is not None, has_cls)
+        ctx.dims = (B, L, keep, G, D, y.dtype, pos_tmp is not None, has_cls, y_row0)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (ids_restore,) = ctx.saved_tensors
-        B, L, keep, G, D, ydt, has_tmp, has_cls = ctx.dims
+        B, L, keep, G, D, ydt, has_tmp, has_cls, y_row0 = ctx.dims
         if not dout.is_contiguous():
             dout = dout.contiguous()
         dev = dout.device
-        dy = torch.empty(B, keep, D, dtype=ydt, device=dev)
+        dy = torch.empty(B, y_row0 + keep, D, dtype=ydt, device=dev)
         d_mt = torch.empty(D, dtype=torch.float32, device=dev)
         d_sp = torch.empty(G, D, dtype=torch.float32, device=dev)
         d_tmp = torch.empty(L // G, D, dtype=torch.float32, device=dev) if has_tmp else None
@@ -519,16 +522,18 @@ class UnshuffleFn(torch.autograd.Function):
         nb = _lib.load().oct_unshuffle_bwd_ws_bytes(B, L, G, D)
         ws = _ws(nb, dev)
         _call("oct_unshuffle_bwd", _p(dout), _p(ids_restore), _p(dy), _dt(dy), _p(d_mt), _p(d_sp), _p(d_tmp), _p(d_cls), _p(ws),
-              ws.numel(), B, L, keep, G, D, 1 if has_cls else 0, _stream())
-        return dy, None, d_mt, d_sp, d_tmp, d_cls
+              ws.numel(), B, L, keep, G, D, 1 if has_cls else 0, y_row0, _stream())
+        return dy, None, d_mt, d_sp, d_tmp, d_cls, None
 
 
 class MaskedMSELossFn(torch.autograd.Function):
     """forward_loss (models:613-667).  pred_full [B, row0 + L, P] (row0 = 1: the cls row is skipped in place).
-    Returns (loss, frame_losses); frame_losses carries no gradient (the engine only logs it, engine_pretrain.py:133-146)."""
+    Returns (loss, frame_losses, loss_tok); frame_losses / loss_tok carry no gradient (the engine only logs them,
+    engine_pretrain.py:133-146).  `extra_flags`: LOSS_CHANNEL_LAST / LOSS_ALL_TOKENS for the 2D model
+    (OCTCube/models_mae_flash_attn.py:331-350; imgs is then the [B,C,H,W] image viewed as [B,1,C,H,W], u = C)."""
 
     @staticmethod
-    def forward(ctx, imgs, pred_full, mask, p, u, row0, norm_pix, frame_idx):
+    def forward(ctx, imgs, pred_full, mask, p, u, row0, norm_pix, frame_idx, extra_flags=0):
         _chk(imgs, pred_full, mask, frame_idx)
         B, _, T, H, W = imgs.shape
         T_sel = T if frame_idx is None else frame_idx.numel()
@@ -539,17 +544,18 @@ class MaskedMSELossFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         msum = torch.empty((), dtype=torch.float32, device=dev)
         frame = torch.empty(B, Tp, dtype=torch.float32, device=dev)
+        flags = (_lib.LOSS_NORM_PIX if norm_pix else 0) | int(extra_flags)
         _call("oct_mse_loss_fwd", _p(imgs), _p(frame_idx), _p(pred_full), _dt(pred_full), _p(mask), _p(loss_tok), _p(loss),
-              _p(msum), _p(frame), B, T, T_sel, H, W, p, u, pred_full.shape[1], row0, 1 if norm_pix else 0, _stream())
+              _p(msum), _p(frame), B, T, T_sel, H, W, p, u, pred_full.shape[1], row0, flags, _stream())
         ctx.save_for_backward(imgs, pred_full, mask, msum, frame_idx if frame_idx is not None else torch.empty(0, device=dev))
-        ctx.cfg = (p, u, row0, norm_pix, frame_idx is not None)
-        ctx.mark_non_differentiable(frame)
-        return loss, frame
+        ctx.cfg = (p, u, row0, flags, frame_idx is not None)
+        ctx.mark_non_differentiable(frame, loss_tok)
+        return loss, frame, loss_tok
 
     @staticmethod
-    def backward(ctx, dloss, _dframe):
+    def backward(ctx, dloss, _dframe, _dtok):
         imgs, pred_full, mask, msum, frame_idx = ctx.saved_tensors
-        p, u, row0, norm_pix, has_idx = ctx.cfg
+        p, u, row0, flags, has_idx = ctx.cfg
         if not has_idx:
             frame_idx = None
         B, _, T, H, W = imgs.shape
@@ -557,8 +563,8 @@ class MaskedMSELossFn(torch.autograd.Function):
         dloss = dloss.to(torch.float32).contiguous()
         dpred = torch.empty_like(pred_full)
         _call("oct_mse_loss_bwd", _p(imgs), _p(frame_idx), _p(pred_full), _dt(pred_full), _p(mask), _p(msum), _p(dloss), _p(dpred),
-              _dt(dpred), B, T, T_sel, H, W, p, u, pred_full.shape[1], row0, 1 if norm_pix else 0, _stream())
-        return None, dpred, None, None, None, None, None, None
+              _dt(dpred), B, T, T_sel, H, W, p, u, pred_full.shape[1], row0, flags, _stream())
+        return None, dpred, None, None, None, None, None, None, None
 
 
 class PatchEmbedFn(torch.autograd.Function):

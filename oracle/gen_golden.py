@@ -8,6 +8,9 @@ Fixtures:
   masking_cases.npz  reference random_masking on noise rows at L in {1024,4096,5120}: natural torch.rand
                      noise and 1/37-quantised noise (ties; argsort forced stable = CUDA radix-sort behaviour,
                      SURVEY H1) and tie-free noise (reference argsort untouched).
+  toy2d_step.npz     the 2D twin (OCTCube/models_mae_flash_attn.py), toy size (E=64/2 heads, D=32/1 head, 3x64x64, B=2, mask
+                     0.75) with norm_pix_loss off and on: images, noise, reference loss / frame_loss / mask / pred / every
+                     parameter gradient.
   full_cfg1.json     ViT-L, 1x48x256x256, mask 0.9 (BASELINE cfg-1): reference loss / mask sum / pred stats
                      for oracle.init_state_dict(seed 0) weights (only with --full; ~1 min).
 """
@@ -21,6 +24,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from oracle import mae2d_oracle as O2  # noqa: E402
 from oracle import mae3d_oracle as O  # noqa: E402
 from oracle import ref_harness as R  # noqa: E402
 
@@ -29,6 +33,39 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 TOY = O.MAEConfig(input_size=64, patch_size=16, in_chans=1, embed_dim=64, depth=2, num_heads=2,
                   decoder_embed_dim=32, decoder_depth=1, decoder_num_heads=1, num_frames=12, t_patch_size=3,
                   pred_t_dim=12, high_res_input_size=128)
+
+
+TOY2D = O2.MAE2DConfig(input_size=64, patch_size=16, in_chans=3, embed_dim=64, depth=2, num_heads=2, decoder_embed_dim=32,
+                       decoder_depth=1, decoder_num_heads=1)
+
+
+def toy2d_inputs():
+    sd = O.perturb_state_dict(O2.init_state_dict(TOY2D, seed=0))
+    return sd, O2.synthetic_images(2, 3, 64, 64, seed=0), O.synthetic_noise(2, TOY2D.num_patches, seed=1)
+
+
+def gen_toy2d():
+    sd, imgs, noise = toy2d_inputs()
+    rec = {"images": imgs.numpy(), "noise": noise.numpy()}
+    for k, v in sd.items():
+        rec["w::" + k] = v.numpy()
+    for norm_pix in (False, True):
+        cfg = O2.MAE2DConfig(**{**TOY2D.__dict__, "norm_pix_loss": norm_pix})
+        m = R.build_reference_2d(**cfg.ref_kwargs())
+        m.load_state_dict(sd, strict=True)
+        out = R.run_reference_2d(m, imgs, noise, 0.75, force_stable_argsort=True, backward=True)
+        tag = "np::" if norm_pix else ""
+        rec[tag + "loss"] = out["loss"].detach().numpy()
+        rec[tag + "frame_loss"] = out["frame_loss"].detach().numpy()
+        rec[tag + "mask"] = out["mask"].numpy()
+        if not norm_pix:
+            rec["pred"] = out["pred"].detach().numpy()
+        for k, v in out["grads"].items():
+            if not norm_pix or k in ("decoder_pred.weight", "blocks.0.mixer.Wqkv.weight", "cls_token", "mask_token",
+                                     "patch_embed.proj.weight"):
+                rec[tag + "g::" + k] = v.numpy()
+        print("toy2d norm_pix", norm_pix, "loss", float(out["loss"]), "mask sum", float(out["mask"].sum()))
+    np.savez_compressed(os.path.join(GOLD, "toy2d_step.npz"), **rec)
 
 
 def toy_inputs():
@@ -102,11 +139,16 @@ def gen_full():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only-2d", action="store_true", help="regenerate toy2d_step.npz only")
     a = ap.parse_args()
+    if a.only_2d:
+        gen_toy2d()
+        sys.exit(0)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     gen_toy(False)
     gen_toy(True)
     gen_masking()
+    gen_toy2d()
     if a.full:
         gen_full()

@@ -73,6 +73,19 @@ def _install_stubs():
         mod("iopath.common.file_io", g_pathmgr=types.SimpleNamespace(open=builtins.open))
     if "simplejson" not in sys.modules:
         sys.modules["simplejson"] = json
+    # the 2D twin (OCTCube/models_mae_flash_attn.py) imports timm's Block by name and util/misc.py, which pulls plotting
+    # packages in at import time; none of it is on the step path
+    vt = sys.modules["timm.models.vision_transformer"]
+    if not hasattr(vt, "Block"):
+        vt.Block = type("Block", (nn.Module,), {})
+    for name in ("matplotlib", "matplotlib.pyplot", "PIL", "PIL.Image", "torchvision", "torchvision.transforms"):
+        try:
+            __import__(name)
+        except Exception:
+            parent, _, leaf = name.rpartition(".")
+            m = mod(name)
+            if parent:
+                setattr(sys.modules[parent], leaf, m)
     if not torch.cuda.is_available():
         # flash_attn/ops/triton/layer_norm.py touches torch.cuda at import time
         sys.modules.setdefault("flash_attn.ops.triton.layer_norm", None)
@@ -118,6 +131,57 @@ def build_reference(flash_semantics=True, seed=0, **kw):
             blk.mixer.inner_attn = SelfAttention()
             blk.mixer.use_flash_attn = False
     return m
+
+
+_REF_MODULE_2D = None
+
+
+def import_reference_2d():
+    """Returns the reference module OCTCube/models_mae_flash_attn (unmodified source; the 2D twin of SURVEY §8a)."""
+    global _REF_MODULE_2D
+    if _REF_MODULE_2D is None:
+        path = os.path.join(REF_ROOT, "OCTCube", "models_mae_flash_attn.py")
+        if not os.path.isfile(path):
+            raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+        _install_stubs()
+        import importlib.util
+
+        p = os.path.join(REF_ROOT, "OCTCube")
+        if p not in sys.path:
+            sys.path.append(p)  # its `from util.… import …` fallbacks resolve against OCTCube/util
+        spec = importlib.util.spec_from_file_location("octcube_ref_models_mae_flash_attn_2d", path)
+        M = importlib.util.module_from_spec(spec)
+        with contextlib.redirect_stdout(open(os.devnull, "w")):
+            spec.loader.exec_module(M)
+        _REF_MODULE_2D = M
+    return _REF_MODULE_2D
+
+
+def build_reference_2d(seed=0, **kw):
+    """The reference's 2D MaskedAutoencoderViT (flash blocks, SelfAttention swapped in) on CPU fp32."""
+    M = import_reference_2d()
+    from functools import partial
+
+    from flash_attn.modules.mha import SelfAttention
+
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(open(os.devnull, "w")):
+        m = M.MaskedAutoencoderViT(norm_layer=partial(nn.LayerNorm, eps=1e-6), use_flash_attn=True, **kw)
+    for blk in list(m.blocks) + list(m.decoder_blocks):
+        blk.mixer.inner_attn = SelfAttention()
+        blk.mixer.use_flash_attn = False
+    return m
+
+
+def run_reference_2d(m, imgs, noise, mask_ratio, force_stable_argsort=False, backward=False):
+    with contextlib.redirect_stdout(open(os.devnull, "w")), inject_noise(noise, force_stable_argsort):
+        loss, pred, mask, frame_loss = m(imgs, mask_ratio=mask_ratio, return_frame_loss=True)
+    out = {"loss": loss, "pred": pred, "mask": mask, "frame_loss": frame_loss}
+    if backward:
+        m.zero_grad(set_to_none=True)
+        loss.backward()
+        out["grads"] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    return out
 
 
 @contextlib.contextmanager

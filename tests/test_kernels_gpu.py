@@ -138,6 +138,30 @@ def test_unshuffle_fwd_bwd(ydtype, Tp):
     assert rel(yd.grad.float(), yr.grad.to(ydtype).float()) < 1e-6
 
 
+@pytest.mark.parametrize("ydtype", [torch.float32, torch.bfloat16])
+def test_unshuffle_per_sample_cls_row(ydtype):
+    """y_row0 = 1: the 2D model's decoder input (OCTCube/models_mae_flash_attn.py:299-312) — row 0 of y is the sample's cls."""
+    B, L, D, keep = 3, 16, 32, 4
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(B, 1 + keep, D, generator=g).to(ydtype)
+    ids_restore = torch.stack([torch.randperm(L, generator=g) for _ in range(B)])
+    mt = torch.randn(D, generator=g, requires_grad=True)
+    pos = torch.randn(1 + L, D, generator=g)
+    yr = y.float().clone().requires_grad_(True)
+    x_ = torch.cat([yr[:, 1:], mt.expand(B, L - keep, D)], 1)
+    x_ = torch.gather(x_, 1, ids_restore[..., None].expand(-1, -1, D))
+    want = torch.cat([yr[:, :1], x_], 1) + pos
+    dout = torch.randn(B, L + 1, D, generator=g)
+    want.backward(dout)
+    yd = y.detach().to(DEV).requires_grad_(True)
+    mtd = mt.detach().to(DEV).requires_grad_(True)
+    got = ops.UnshuffleFn.apply(yd, ids_restore.to(DEV), mtd, pos[1:].contiguous().to(DEV), None, pos[0].contiguous().to(DEV), 1)
+    assert rel(got, want.detach()) < 1e-6
+    got.backward(dout.to(DEV))
+    assert rel(mtd.grad, mt.grad) < 1e-5
+    assert rel(yd.grad.float(), yr.grad.to(ydtype).float()) < 1e-6
+
+
 # ---------------------------------------------------------------- add + LayerNorm
 @pytest.mark.parametrize("C", [32, 64, 512, 1024, 1280])
 @pytest.mark.parametrize("hdtype,ydtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
@@ -226,12 +250,38 @@ def test_mse_loss_fwd_bwd(norm_pix, pdtype):
     loss_ref, fl_ref = O.forward_loss(cfg, imgs, pr[:, 1:], mask, frame_loss=True)
     (loss_ref * 1.7).backward()
     pd = pred_full.detach().to(DEV).requires_grad_(True)
-    loss, fl = ops.MaskedMSELossFn.apply(imgs.to(DEV), pd, mask.to(DEV), 16, 3, 1, norm_pix, None)
+    loss, fl, _ = ops.MaskedMSELossFn.apply(imgs.to(DEV), pd, mask.to(DEV), 16, 3, 1, norm_pix, None)
     assert abs(float(loss) - float(loss_ref)) < 2e-6 * abs(float(loss_ref))
     assert rel(fl, fl_ref.detach()) < 1e-5
     (loss * 1.7).backward()
     assert rel(pd.grad.float(), pr.grad) < (1e-5 if pdtype == torch.float32 else 5e-3)
     assert float(pd.grad[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("norm_pix", [False, True])
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
+def test_mse_loss_channel_last_2d(norm_pix, pdtype):
+    """The 2D model's loss (OCTCube/models_mae_flash_attn.py:331-350): (p, q, c) patch order, frame_loss over ALL patches."""
+    from octcubem_b200._lib import LOSS_ALL_TOKENS, LOSS_CHANNEL_LAST
+    from oracle import mae2d_oracle as O2
+    cfg = O2.MAE2DConfig(input_size=64, norm_pix_loss=norm_pix)
+    B, L, P = 2, 16, 768
+    g = torch.Generator().manual_seed(6)
+    imgs = O2.synthetic_images(B, 3, 64, 64, seed=3)
+    pred_full = torch.randn(B, L + 1, P, generator=g).to(pdtype)
+    mask = (torch.rand(B, L, generator=g) > 0.3).float()
+    pr = pred_full.float().clone().requires_grad_(True)
+    loss_ref, fl_ref = O2.forward_loss(cfg, imgs, pr[:, 1:], mask, return_frame_loss=True)
+    (loss_ref * 0.6).backward()
+    pd = pred_full.detach().to(DEV).requires_grad_(True)
+    vol = imgs.view(B, 1, 3, 64, 64).to(DEV)
+    loss, _, tok = ops.MaskedMSELossFn.apply(vol, pd, mask.to(DEV), 16, 3, 1, norm_pix, None, LOSS_CHANNEL_LAST | LOSS_ALL_TOKENS)
+    assert abs(float(loss) - float(loss_ref)) < 2e-6 * abs(float(loss_ref))
+    assert rel(tok.mean(-1), fl_ref.detach()) < 1e-5
+    (loss * 0.6).backward()
+    assert rel(pd.grad.float(), pr.grad) < (1e-5 if pdtype == torch.float32 else 5e-3)
+    loss_m, _, tok_m = ops.MaskedMSELossFn.apply(vol, pd.detach(), mask.to(DEV), 16, 3, 1, norm_pix, None, LOSS_CHANNEL_LAST)
+    assert float(loss_m) == float(loss) and bool((tok_m[mask.to(DEV) == 0] == 0).all())   # masked-only mode: same loss
 
 
 def test_mse_loss_frame_index_select():
@@ -243,7 +293,7 @@ def test_mse_loss_frame_index_select():
     mask = torch.ones(1, L)
     want = O.forward_loss(cfg, imgs, pred, mask)
     fidx = torch.linspace(0, 11, 6).long()
-    loss, _ = ops.MaskedMSELossFn.apply(imgs.to(DEV), pred.to(DEV), mask.to(DEV), 16, 1, 0, False, fidx.to(DEV))
+    loss, _, _ = ops.MaskedMSELossFn.apply(imgs.to(DEV), pred.to(DEV), mask.to(DEV), 16, 1, 0, False, fidx.to(DEV))
     assert abs(float(loss) - float(want)) < 2e-6 * abs(float(want))
 
 

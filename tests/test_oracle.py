@@ -7,9 +7,10 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import mae2d_oracle as O2
 from oracle import mae3d_oracle as O
 from oracle import ref_harness as R
-from oracle.gen_golden import TOY, toy_inputs
+from oracle.gen_golden import TOY, TOY2D, toy2d_inputs, toy_inputs
 
 needs_ref = pytest.mark.skipif(not R.reference_available(), reason="/root/reference not present")
 
@@ -136,6 +137,68 @@ def test_cpu_baseline_restatement_vs_reference_nonflash():
     assert torch.equal(mask, ref["mask"])
     assert abs(float(loss) - float(ref["loss"])) < 1e-6
     assert _rel(pred, ref["pred"]) < 1e-6
+
+
+# ---------------------------------------------------------------- 2D twin (OCTCube/models_mae_flash_attn.py)
+@pytest.mark.parametrize("norm_pix", [False, True])
+def test_toy2d_step_golden(golden_dir, norm_pix):
+    g = np.load(os.path.join(golden_dir, "toy2d_step.npz"))
+    tag = "np::" if norm_pix else ""
+    cfg = O2.MAE2DConfig(**{**TOY2D.__dict__, "norm_pix_loss": norm_pix})
+    sd, imgs, noise = toy2d_inputs()
+    assert np.array_equal(imgs.numpy(), g["images"]) and np.array_equal(noise.numpy(), g["noise"])
+    for k, v in sd.items():
+        assert np.array_equal(v.numpy(), g["w::" + k]), k
+    (loss, pred, mask, frame_loss), grads = O2.forward_backward(cfg, sd, imgs, 0.75, noise)
+    assert abs(float(loss) - float(g[tag + "loss"])) <= 1e-6 * abs(float(g[tag + "loss"]))
+    assert np.array_equal(mask.numpy(), g[tag + "mask"]) and float(mask.sum()) == 2 * (16 - 4)
+    assert _rel(frame_loss.detach(), g[tag + "frame_loss"]) < 1e-6
+    if not norm_pix:
+        assert _rel(pred.detach(), g["pred"]) < 1e-6
+        # the two sin-cos tables are frozen (models_mae_flash_attn.py:97,143); everything else gets a gradient
+        assert set(sd) - set(grads) == set(O2.FROZEN)
+        assert {k[3:] for k in g.files if k.startswith("g::")} == set(grads)
+    n = 0
+    for k in g.files:
+        if k.startswith(tag + "g::"):
+            assert _rel(grads[k[len(tag) + 3:]], g[k]) < 2e-5, k
+            n += 1
+    assert n >= 5
+
+
+def test_2d_patch_order_and_conv_view():
+    imgs = torch.randn(2, 3, 64, 64)
+    p = O2.patchify(imgs, 16)
+    assert p.shape == (2, 16, 768) and torch.equal(O2.unpatchify(p, 16), imgs)
+    # element order is (p, q, c): the first three values of a patch are the three channels of its top-left pixel
+    assert torch.equal(p[0, 5, :3], imgs[0, :, 16, 16])
+    # a [B,3,H,W] image is a [B,1,3,H,W] volume with t_patch 3 for the patch-embed GEMM (same K = 768 order as the
+    # Conv2d weight [E,3,16,16]) — the identity the CUDA path relies on
+    w, b = torch.randn(32, 3, 16, 16), torch.randn(32)
+    want = torch.nn.functional.conv2d(imgs, w, b, stride=16).flatten(2).transpose(1, 2)
+    got = O.patchify(imgs.view(2, 1, 3, 64, 64), 16, 3) @ w.view(32, -1).t() + b
+    assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)
+
+
+@needs_ref
+def test_oracle2d_vs_reference_tiefree_unpatched_argsort():
+    """The unmodified 2D reference (its own torch.argsort, its own sin-cos tables) on tie-free noise == oracle."""
+    cfg = TOY2D
+    m = R.build_reference_2d(**cfg.ref_kwargs())
+    fresh = O2.init_state_dict(cfg)
+    assert torch.equal(m.pos_embed, fresh["pos_embed"]) and torch.equal(m.decoder_pos_embed, fresh["decoder_pos_embed"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in fresh.items()}
+    sd, imgs, _ = toy2d_inputs()
+    noise = O.synthetic_noise(2, cfg.num_patches, seed=5, tie_free=True)
+    m.load_state_dict(sd, strict=True)
+    ref = R.run_reference_2d(m, imgs, noise, 0.75, backward=True)
+    (loss, pred, mask, frame_loss), grads = O2.forward_backward(cfg, sd, imgs, 0.75, noise)
+    assert torch.equal(mask, ref["mask"])
+    assert abs(float(loss) - float(ref["loss"])) < 1e-6
+    assert _rel(pred.detach(), ref["pred"].detach()) < 1e-6 and _rel(frame_loss.detach(), ref["frame_loss"].detach()) < 1e-6
+    assert set(grads) == set(ref["grads"])
+    for k in grads:
+        assert _rel(grads[k], ref["grads"][k]) < 2e-5, k
 
 
 @pytest.mark.slow
