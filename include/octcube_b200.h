@@ -132,7 +132,8 @@ int oct_attn_bwd(int compute, const void* qkv, const void* out, const void* dout
 int oct_gelu_fwd(const void* x, void* y, int dtype, int64_t n, oct_stream_t stream);
 int oct_gelu_bwd(const void* dy, const void* x, void* dx, int dtype, int64_t n, oct_stream_t stream);
 
-/* ---- bias gradient: out[n] (= or +=) sum_m x[m,n] ; x [M,ldx] f32|bf16 ; deterministic two-stage ------------ */
+/* ---- bias gradient: out[n] (= or +=) sum_m x[m,n] ; x [M,ldx] f32|bf16 ; deterministic two-stage (N, ldx multiples of 4;
+ * any other width takes a one-thread-per-column path) ------------------------------------------------------------ */
 size_t oct_colsum_ws_bytes(int64_t M, int64_t N);
 int oct_colsum(const void* x, int x_dtype, float* out, int64_t M, int64_t N, int64_t ldx, int beta, void* ws,
                size_t ws_bytes, oct_stream_t stream);
@@ -174,6 +175,17 @@ int oct_mse_loss_bwd(const float* imgs, const int64_t* frame_idx, const void* pr
                      const float* mask_sum, const float* dloss, void* dpred, int dpred_dtype, int64_t B, int64_t T,
                      int64_t T_sel, int64_t H, int64_t W, int64_t p, int64_t u, int64_t pred_rows, int64_t pred_row0,
                      int flags, oct_stream_t stream);
+
+/* ---- token pooling of the encoder-only ViT (OCTCube/models_vit_st_flash_attn.py:247-251) ------------------------
+ * out[b,:] = mean over s in [row0, row1) of x[b,s,:] : `x[:, 1:, :].mean(dim=1)` (row0 = 1, row1 = S: global pool without the
+ * cls token) or `x[:, 0]` (row0 = 0, row1 = 1).  x [B,S,C] f32|bf16, out [B,C] f32|bf16, fp32 accumulation in a fixed order.
+ * ws >= oct_mean_pool_ws_bytes(B,C,row0,row1). */
+size_t oct_mean_pool_ws_bytes(int64_t B, int64_t C, int64_t row0, int64_t row1);
+int oct_mean_pool_fwd(const void* x, int x_dtype, void* out, int out_dtype, int64_t B, int64_t S, int64_t C, int64_t row0,
+                      int64_t row1, void* ws, size_t ws_bytes, oct_stream_t stream);
+/* dx[b,s,:] = dout[b,:] / (row1 - row0) for s in [row0, row1), 0 for the other rows */
+int oct_mean_pool_bwd(const void* dout, int dout_dtype, void* dx, int dx_dtype, int64_t B, int64_t S, int64_t C, int64_t row0,
+                      int64_t row1, oct_stream_t stream);
 
 /* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
 int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);

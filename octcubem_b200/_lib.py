@@ -48,6 +48,9 @@ SIGNATURES = {
     "oct_unshuffle_bwd": (I, [P, P, P, I, P, P, P, P, P, Z, L, L, L, L, L, I, L, P]),
     "oct_mse_loss_fwd": (I, [P, P, P, I, P, P, P, P, P, L, L, L, L, L, L, L, L, L, I, P]),
     "oct_mse_loss_bwd": (I, [P, P, P, I, P, P, P, P, I, L, L, L, L, L, L, L, L, L, I, P]),
+    "oct_mean_pool_ws_bytes": (Z, [L, L, L, L]),
+    "oct_mean_pool_fwd": (I, [P, I, P, I, L, L, L, L, L, P, Z, P]),
+    "oct_mean_pool_bwd": (I, [P, I, P, I, L, L, L, L, L, P]),
     "oct_cast_f32_to_bf16": (I, [P, P, L, P]),
     "oct_adamw_step": (I, [P, L, F, F, F, F, F, L, F, P, P]),
     "oct_grad_norm": (I, [P, L, F, F, P, P, P]),

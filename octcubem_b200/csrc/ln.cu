@@ -571,6 +571,15 @@ __global__ void colsum_finish_kernel(const float* __restrict__ ws, float* __rest
   for (int s = 0; s < slices; ++s) a += ws[(size_t)s * N + c];
   out[c] = beta ? out[c] + a : a;
 }
+// any N / ldx (classifier heads with a handful of classes): one thread per column, rows in order
+template <typename T>
+__global__ void colsum_scalar_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t M, int N, int64_t ldx, int beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float a = 0.f;
+  for (int64_t r = 0; r < M; ++r) a += ldf<T>(x + r * ldx + c);
+  out[c] = beta ? out[c] + a : a;
+}
 static int colsum_slices(int64_t M) {
   int64_t s = ceil_div64(M, 128);   // >= 128 rows (16 per row lane) per slice
   if (s > 296) s = 296;             // 2 slices per SM at most
@@ -580,10 +589,16 @@ extern "C" size_t oct_colsum_ws_bytes(int64_t M, int64_t N) { return (size_t)col
 extern "C" int oct_colsum(const void* x, int x_dtype, float* out, int64_t M, int64_t N, int64_t ldx, int beta, void* ws,
                           size_t ws_bytes, oct_stream_t stream) {
   OCT_REQUIRE(x && out, "oct_colsum: null pointer");
-  OCT_REQUIRE(N % 4 == 0 && ldx % 4 == 0, "oct_colsum: N and ldx must be multiples of 4");
+  OCT_REQUIRE(x_dtype == OCT_F32 || x_dtype == OCT_BF16, "oct_colsum: bad dtype");
   if (!ws || ws_bytes < oct_colsum_ws_bytes(M, N)) { oct_set_error("oct_colsum: workspace too small"); return OCT_ERR_WORKSPACE; }
   if (N == 0) return OCT_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (N % 4 != 0 || ldx % 4 != 0 || (x_dtype == OCT_F32 ? !aligned16(x) : (reinterpret_cast<uintptr_t>(x) & 7) != 0)) {
+    const unsigned g = (unsigned)ceil_div64(N, 128);
+    if (x_dtype == OCT_F32) colsum_scalar_kernel<float><<<g, 128, 0, st>>>((const float*)x, out, M, (int)N, ldx, beta);
+    else colsum_scalar_kernel<__nv_bfloat16><<<g, 128, 0, st>>>((const __nv_bfloat16*)x, out, M, (int)N, ldx, beta);
+    return oct_check_launch("oct_colsum(scalar)");
+  }
   const int slices = colsum_slices(M);
   const int64_t rps = ceil_div64(M > 0 ? M : 1, slices);
   dim3 grid((unsigned)ceil_div64(N, 128), (unsigned)slices), block(32, kCsRows);

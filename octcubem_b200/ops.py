@@ -567,6 +567,30 @@ class MaskedMSELossFn(torch.autograd.Function):
         return None, dpred, None, None, None, None, None, None, None
 
 
+class MeanPoolFn(torch.autograd.Function):
+    """x[:, row0:row1, :].mean(dim=1) -> [B, C] in `out_dtype` (OCTCube/models_vit_st_flash_attn.py:247-251: global pool
+    without the cls token = rows [1, S); the cls read-out `x[:, 0]` = rows [0, 1))."""
+
+    @staticmethod
+    def forward(ctx, x, row0, row1, out_dtype):
+        _chk(x)
+        B, S, C = x.shape
+        out = torch.empty(B, C, dtype=out_dtype, device=x.device)
+        ws = _ws(_lib.load().oct_mean_pool_ws_bytes(B, C, row0, row1), x.device)
+        _call("oct_mean_pool_fwd", _p(x), _dt(x), _p(out), _dt(out), B, S, C, row0, row1, _p(ws), ws.numel(), _stream())
+        ctx.dims = (B, S, C, row0, row1, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, S, C, row0, row1, xdt = ctx.dims
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dx = torch.empty(B, S, C, dtype=xdt, device=dout.device)
+        _call("oct_mean_pool_bwd", _p(dout), _dt(dout), _p(dx), _dt(dx), B, S, C, row0, row1, _stream())
+        return dx, None, None, None
+
+
 class PatchEmbedFn(torch.autograd.Function):
     """Standalone PatchEmbed.forward (vv:74-83) -> [B, T'*h*w, E] with a dense backward (wgrad over all tokens)."""
 

@@ -11,6 +11,9 @@ Fixtures:
   toy2d_step.npz     the 2D twin (OCTCube/models_mae_flash_attn.py), toy size (E=64/2 heads, D=32/1 head, 3x64x64, B=2, mask
                      0.75) with norm_pix_loss off and on: images, noise, reference loss / frame_loss / mask / pred / every
                      parameter gradient.
+  toy_vit_step.npz   the encoder-only ViT (OCTCube/models_vit_st_flash_attn.py), toy size (E=64/2 heads, 12x64x64, B=2, 5 classes),
+                     eval mode: "sep::" = separable pos + cls + global pool, "joint::" = joint pos table + cls read-out:
+                     volume, dlogits, reference logits / embedding / last hidden state / every parameter gradient.
   full_cfg1.json     ViT-L, 1x48x256x256, mask 0.9 (BASELINE cfg-1): reference loss / mask sum / pred stats
                      for oracle.init_state_dict(seed 0) weights (only with --full; ~1 min).
 """
@@ -27,6 +30,7 @@ sys.path.insert(0, ROOT)
 from oracle import mae2d_oracle as O2  # noqa: E402
 from oracle import mae3d_oracle as O  # noqa: E402
 from oracle import ref_harness as R  # noqa: E402
+from oracle import vit_st_oracle as OV  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -66,6 +70,41 @@ def gen_toy2d():
                 rec[tag + "g::" + k] = v.numpy()
         print("toy2d norm_pix", norm_pix, "loss", float(out["loss"]), "mask sum", float(out["mask"].sum()))
     np.savez_compressed(os.path.join(GOLD, "toy2d_step.npz"), **rec)
+
+
+TOY_VIT = {"sep": OV.ViTConfig(num_frames=12, t_patch_size=3, img_size=64, num_classes=5, embed_dim=64, depth=2, num_heads=2,
+                               sep_pos_embed=True, cls_embed=True, global_pool=True),
+           "joint": OV.ViTConfig(num_frames=12, t_patch_size=3, img_size=64, num_classes=5, embed_dim=64, depth=2, num_heads=2,
+                                 sep_pos_embed=False, cls_embed=True, global_pool=False)}
+
+
+def toy_vit_inputs(kind):
+    sd = OV.init_state_dict(TOY_VIT[kind], seed=0)
+    vol = O.synthetic_volume(2, 12, 64, 64, seed=0, zero_pad_frames=1)
+    dlogits = torch.randn(2, 5, generator=torch.Generator().manual_seed(3))
+    return sd, vol, dlogits
+
+
+def gen_toy_vit():
+    rec = {}
+    for kind, cfg in TOY_VIT.items():
+        sd, vol, dlogits = toy_vit_inputs(kind)
+        m = R.build_reference_vit(**cfg.ref_kwargs())
+        m.load_state_dict(sd, strict=True)
+        logits, emb = m(vol, return_embeddings=True)
+        m.zero_grad(set_to_none=True)
+        logits.backward(dlogits)
+        with torch.no_grad():
+            hidden = m(vol, hidden_states=True)
+        rec[kind + "::volume"], rec[kind + "::dlogits"] = vol.numpy(), dlogits.numpy()
+        rec[kind + "::logits"], rec[kind + "::embedding"] = logits.detach().numpy(), emb.detach().numpy()
+        rec[kind + "::hidden_last"] = hidden[-1].numpy()
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                rec[f"{kind}::g::{k}"] = p.grad.numpy()
+        print("toy vit", kind, "logits", logits.detach().flatten()[:3].tolist(),
+              "no grad:", [k for k, p in m.named_parameters() if p.grad is None])
+    np.savez_compressed(os.path.join(GOLD, "toy_vit_step.npz"), **rec)
 
 
 def toy_inputs():
@@ -140,9 +179,13 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--only-2d", action="store_true", help="regenerate toy2d_step.npz only")
+    ap.add_argument("--only-vit", action="store_true", help="regenerate toy_vit_step.npz only")
     a = ap.parse_args()
     if a.only_2d:
         gen_toy2d()
+        sys.exit(0)
+    if a.only_vit:
+        gen_toy_vit()
         sys.exit(0)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -150,5 +193,6 @@ if __name__ == "__main__":
     gen_toy(True)
     gen_masking()
     gen_toy2d()
+    gen_toy_vit()
     if a.full:
         gen_full()

@@ -184,6 +184,46 @@ def run_reference_2d(m, imgs, noise, mask_ratio, force_stable_argsort=False, bac
     return out
 
 
+_REF_MODULE_VIT = None
+
+
+def import_reference_vit():
+    """Returns the reference module OCTCube/models_vit_st_flash_attn (unmodified source)."""
+    global _REF_MODULE_VIT
+    if _REF_MODULE_VIT is None:
+        path = os.path.join(REF_ROOT, "OCTCube", "models_vit_st_flash_attn.py")
+        if not os.path.isfile(path):
+            raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+        _install_stubs()
+        import importlib.util
+
+        p = os.path.join(REF_ROOT, "OCTCube")
+        if p not in sys.path:
+            sys.path.append(p)
+        spec = importlib.util.spec_from_file_location("octcube_ref_models_vit_st_flash_attn", path)
+        M = importlib.util.module_from_spec(spec)
+        with contextlib.redirect_stdout(open(os.devnull, "w")):
+            spec.loader.exec_module(M)
+        _REF_MODULE_VIT = M
+    return _REF_MODULE_VIT
+
+
+def build_reference_vit(seed=0, **kw):
+    """The reference's encoder-only VisionTransformer (flash blocks, SelfAttention swapped in) on CPU fp32, eval mode."""
+    M = import_reference_vit()
+    from functools import partial
+
+    from flash_attn.modules.mha import SelfAttention
+
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(open(os.devnull, "w")):
+        m = M.VisionTransformer(norm_layer=partial(nn.LayerNorm, eps=1e-6), use_flash_attn=True, **kw)
+    for blk in m.blocks:
+        blk.mixer.inner_attn = SelfAttention()
+        blk.mixer.use_flash_attn = False
+    return m.eval()
+
+
 @contextlib.contextmanager
 def inject_noise(noise, force_stable_argsort=False):
     """Replaces torch.rand(N, L, device=...) (the only call shape in random_masking,

@@ -236,6 +236,14 @@ def test_gelu_colsum_cast():
     assert torch.equal(ops.cast_bf16(odd.to(DEV)).cpu(), odd.bfloat16())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum_unaligned_width(dtype):
+    """classifier heads: N not a multiple of 4 takes the scalar path of oct_colsum."""
+    x = torch.randn(37, 5, generator=torch.Generator().manual_seed(0)).to(dtype)
+    got = ops.colsum(x.to(DEV))
+    assert rel(got, x.float().sum(0)) < 1e-6
+
+
 # ---------------------------------------------------------------- loss
 @pytest.mark.parametrize("norm_pix", [False, True])
 @pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])

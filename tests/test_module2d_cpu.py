@@ -68,3 +68,36 @@ def test_checkpoint_key_surgery():
 
 def test_factories():
     assert M2.mae_vit_large_patch16 is M2.mae_vit_large_patch16_dec512d8b
+
+
+# ---------------------------------------------------------------- encoder-only ViT surface
+def test_vit_state_dict_surface_and_key_surgery():
+    from octcubem_b200 import models_vit_st_flash_attn as MV
+    from oracle import vit_st_oracle as OV
+    from oracle.gen_golden import TOY_VIT
+    for kind, cfg in TOY_VIT.items():
+        m = MV.VisionTransformer(**cfg.ref_kwargs(), use_flash_attn=True, some_unknown_flag=3,
+                                 norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6))
+        sd = OV.init_state_dict(cfg)
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}, kind
+        m.load_state_dict(sd, strict=True)
+        assert m.no_weight_decay() >= {"cls_token", "pos_embed_spatial"}
+        timm_style = {}
+        for k, v in sd.items():
+            if ".mixer.Wqkv." in k:
+                for i, n in enumerate("qkv"):
+                    timm_style[k.replace("mixer.Wqkv", f"attn.{n}")] = v.chunk(3, 0)[i]
+            elif ".mixer.out_proj." in k:
+                timm_style[k.replace("mixer.out_proj", "attn.proj")] = v
+            else:
+                timm_style[k] = v
+        for p in m.parameters():
+            p.data.zero_()
+        res = m.load_state_dict_to_backbone(timm_style, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+    with pytest.raises(NotImplementedError):
+        MV.VisionTransformer(num_frames=12, t_patch_size=3, use_flash_attn=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.rand(2, 1, 12, 64, 64))

@@ -10,7 +10,8 @@ import torch
 from oracle import mae2d_oracle as O2
 from oracle import mae3d_oracle as O
 from oracle import ref_harness as R
-from oracle.gen_golden import TOY, TOY2D, toy2d_inputs, toy_inputs
+from oracle import vit_st_oracle as OV
+from oracle.gen_golden import TOY, TOY2D, TOY_VIT, toy2d_inputs, toy_inputs, toy_vit_inputs
 
 needs_ref = pytest.mark.skipif(not R.reference_available(), reason="/root/reference not present")
 
@@ -199,6 +200,44 @@ def test_oracle2d_vs_reference_tiefree_unpatched_argsort():
     assert set(grads) == set(ref["grads"])
     for k in grads:
         assert _rel(grads[k], ref["grads"][k]) < 2e-5, k
+
+
+# ---------------------------------------------------------------- encoder-only ViT (OCTCube/models_vit_st_flash_attn.py)
+@pytest.mark.parametrize("kind", ["sep", "joint"])
+def test_toy_vit_golden(golden_dir, kind):
+    g = np.load(os.path.join(golden_dir, "toy_vit_step.npz"))
+    cfg = TOY_VIT[kind]
+    sd, vol, dlogits = toy_vit_inputs(kind)
+    assert np.array_equal(vol.numpy(), g[kind + "::volume"]) and np.array_equal(dlogits.numpy(), g[kind + "::dlogits"])
+    (logits, emb), grads = OV.forward_backward(cfg, sd, vol, dlogits)
+    assert _rel(logits.detach(), g[kind + "::logits"]) < 1e-6 and _rel(emb.detach(), g[kind + "::embedding"]) < 1e-6
+    with torch.no_grad():
+        assert _rel(OV.forward(cfg, sd, vol, hidden_states=True)[-1], g[kind + "::hidden_last"]) < 1e-6
+    want = {k[len(kind) + 5:]: g[k] for k in g.files if k.startswith(kind + "::g::")}
+    assert set(want) == set(grads) == set(sd) - {"norm.weight", "norm.bias"}   # the final norm is dead code (:249)
+    for k in want:
+        assert _rel(grads[k], want[k]) < 2e-5, k
+
+
+@needs_ref
+@pytest.mark.parametrize("sep,cls,gp", [(True, True, True), (False, True, False), (True, False, True)])
+def test_vit_oracle_vs_reference(sep, cls, gp):
+    cfg = OV.ViTConfig(num_frames=12, t_patch_size=3, img_size=64, num_classes=5, embed_dim=64, depth=2, num_heads=2,
+                       sep_pos_embed=sep, cls_embed=cls, global_pool=gp)
+    m = R.build_reference_vit(**cfg.ref_kwargs())
+    sd = OV.init_state_dict(cfg, seed=4)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    m.load_state_dict(sd, strict=True)
+    vol = O.synthetic_volume(2, 12, 64, 64, seed=9, zero_pad_frames=1)
+    dlogits = torch.randn(2, 5, generator=torch.Generator().manual_seed(1))
+    logits, emb = m(vol, return_embeddings=True)
+    logits.backward(dlogits)
+    ref_g = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    (l2, e2), g2 = OV.forward_backward(cfg, sd, vol, dlogits)
+    assert _rel(l2.detach(), logits.detach()) < 1e-6 and _rel(e2.detach(), emb.detach()) < 1e-6
+    assert set(g2) == set(ref_g)
+    for k in g2:
+        assert _rel(g2[k], ref_g[k]) < 2e-5, k
 
 
 @pytest.mark.slow
