@@ -199,6 +199,18 @@ int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t st
 int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                    int64_t step, float grad_scale, const float* grad_scale_dev, oct_stream_t stream);
 
+/* Device-resident optimizer clock for CUDA-graph replay: `clock` = 16 bytes on the device {int32 step, f32 lr, f32 1-beta1^step,
+ * f32 sqrt(1-beta2^step)}, zero-initialised by the caller.  oct_adamw_clock_advance (one thread, inside the captured step)
+ * increments step and evaluates the reference's per-iteration half-cycle cosine (custom_util/lr_sched.py:10-28) at the
+ * fractional epoch e = (step-1) * epochs_per_step (epochs_per_step = accum_iter / len(data_loader), engine_pretrain.py:87-91):
+ * lr = base_lr * e / warmup_epochs while e < warmup_epochs, else min_lr + (base_lr - min_lr) * (1 + cos(pi (e - warmup) /
+ * (epochs - warmup))) / 2.  oct_adamw_step_clocked is oct_adamw_step with lr = lr_scale * clock.lr and the bias corrections
+ * read from the clock, so that replaying the same launch parameters performs consecutive optimizer steps. */
+int oct_adamw_clock_advance(void* clock, float base_lr, float min_lr, float warmup_epochs, float epochs, float epochs_per_step,
+                            float beta1, float beta2, oct_stream_t stream);
+int oct_adamw_step_clocked(const int64_t* table, int64_t n_chunks, const void* clock, float lr_scale, float beta1, float beta2,
+                           float eps, float weight_decay, float grad_scale, const float* grad_scale_dev, oct_stream_t stream);
+
 /* global L2 norm of the gradients in `table` (same rows as oct_adamw_step; several groups = several tables concatenated by the
  * caller) — misc.py:356-373: out[0] = grad_scale * ||g||_2 ; out[1] = max_norm > 0 ? min(1, max_norm / (out[0] + 1e-6)) : 1.
  * partial: n_chunks floats of workspace; deterministic two-stage sum; nothing is copied to the host. */

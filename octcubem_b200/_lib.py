@@ -53,6 +53,8 @@ SIGNATURES = {
     "oct_mean_pool_bwd": (I, [P, I, P, I, L, L, L, L, L, P]),
     "oct_cast_f32_to_bf16": (I, [P, P, L, P]),
     "oct_adamw_step": (I, [P, L, F, F, F, F, F, L, F, P, P]),
+    "oct_adamw_clock_advance": (I, [P, F, F, F, F, F, F, F, P]),
+    "oct_adamw_step_clocked": (I, [P, L, P, F, F, F, F, F, F, P, P]),
     "oct_grad_norm": (I, [P, L, F, F, P, P, P]),
 }
 

@@ -25,7 +25,39 @@ __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, co
   p -= (a.lr / a.bias_corr1) * (m / denom);
 }
 
-__global__ void __launch_bounds__(256) adamw_multi_kernel(const int64_t* __restrict__ table, int n_chunks, AdamWArgs a) {
+// Device-resident optimizer clock (16 bytes): a captured CUDA graph replays the SAME launch parameters every step, so the
+// quantities that change per step — the step count behind the bias corrections and the per-iteration cosine learning rate of
+// custom_util/lr_sched.py:10-28 — live on the device and are advanced by a one-thread kernel inside the graph.
+struct AdamWClock {
+  int step;               // optimizer steps taken (1-based after the first advance)
+  float lr;               // learning rate of this step (before a group's lr_scale)
+  float bias_corr1;       // 1 - beta1^step
+  float bias_corr2_sqrt;  // sqrt(1 - beta2^step)
+};
+
+__global__ void adamw_clock_advance_kernel(AdamWClock* clk, float base_lr, float min_lr, float warmup_epochs, float epochs,
+                                           float epochs_per_step, float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int step = clk->step + 1;
+  // lr_sched.adjust_learning_rate at the fractional epoch of the accumulation group's first iteration
+  const double e = (double)(step - 1) * (double)epochs_per_step;
+  double lr;
+  if (e < (double)warmup_epochs) lr = (double)base_lr * e / (double)warmup_epochs;
+  else lr = (double)min_lr + ((double)base_lr - (double)min_lr) * 0.5 *
+                             (1.0 + cos(3.14159265358979323846 * (e - (double)warmup_epochs) / ((double)epochs - (double)warmup_epochs)));
+  clk->step = step;
+  clk->lr = (float)lr;
+  clk->bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
+  clk->bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const int64_t* __restrict__ table, int n_chunks, AdamWArgs a,
+                                                          const AdamWClock* __restrict__ clk) {
+  if (clk) {  // a.lr carries the group's lr_scale
+    a.lr *= clk->lr;
+    a.bias_corr1 = clk->bias_corr1;
+    a.bias_corr2_sqrt = clk->bias_corr2_sqrt;
+  }
   if (a.grad_scale_dev) a.grad_scale *= __ldg(a.grad_scale_dev);
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int64_t* row = table + 6 * (int64_t)c;
@@ -122,6 +154,35 @@ extern "C" int oct_adamw_step(const int64_t* table, int64_t n_chunks, float lr, 
   a.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   const int64_t cap = (int64_t)oct_num_sms() * 8;
-  adamw_multi_kernel<<<(unsigned)(n_chunks < cap ? n_chunks : cap), 256, 0, (cudaStream_t)stream>>>(table, (int)n_chunks, a);
+  adamw_multi_kernel<<<(unsigned)(n_chunks < cap ? n_chunks : cap), 256, 0, (cudaStream_t)stream>>>(table, (int)n_chunks, a,
+                                                                                                  nullptr);
   return oct_check_launch("oct_adamw_step");
+}
+
+extern "C" int oct_adamw_clock_advance(void* clock, float base_lr, float min_lr, float warmup_epochs, float epochs,
+                                       float epochs_per_step, float beta1, float beta2, oct_stream_t stream) {
+  OCT_REQUIRE(clock && aligned16(clock), "oct_adamw_clock_advance: clock must be a 16-byte aligned device buffer");
+  OCT_REQUIRE(epochs > warmup_epochs && warmup_epochs >= 0.f && epochs_per_step >= 0.f, "oct_adamw_clock_advance: bad schedule");
+  OCT_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "oct_adamw_clock_advance: bad betas");
+  adamw_clock_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((AdamWClock*)clock, base_lr, min_lr, warmup_epochs, epochs,
+                                                                 epochs_per_step, beta1, beta2);
+  return oct_check_launch("oct_adamw_clock_advance");
+}
+
+extern "C" int oct_adamw_step_clocked(const int64_t* table, int64_t n_chunks, const void* clock, float lr_scale, float beta1,
+                                      float beta2, float eps, float weight_decay, float grad_scale, const float* grad_scale_dev,
+                                      oct_stream_t stream) {
+  OCT_REQUIRE(table || n_chunks == 0, "oct_adamw_step_clocked: null table");
+  OCT_REQUIRE(clock, "oct_adamw_step_clocked: null clock");
+  OCT_REQUIRE(n_chunks >= 0 && n_chunks < (1 << 30), "oct_adamw_step_clocked: bad chunk count");
+  OCT_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "oct_adamw_step_clocked: bad hyper-parameters");
+  if (n_chunks == 0) return OCT_OK;
+  AdamWArgs a;
+  a.lr = lr_scale; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  a.grad_scale_dev = grad_scale_dev;
+  a.bias_corr1 = 1.f; a.bias_corr2_sqrt = 1.f;  // read from the clock
+  const int64_t cap = (int64_t)oct_num_sms() * 8;
+  adamw_multi_kernel<<<(unsigned)(n_chunks < cap ? n_chunks : cap), 256, 0, (cudaStream_t)stream>>>(table, (int)n_chunks, a,
+                                                                                                  (const AdamWClock*)clock);
+  return oct_check_launch("oct_adamw_step_clocked");
 }

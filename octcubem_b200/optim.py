@@ -43,15 +43,43 @@ def adjust_learning_rate(optimizer, epoch, lr, min_lr, warmup_epochs, epochs):
     return cur
 
 
+class CosineSchedule:
+    """The reference's per-iteration learning-rate rule (lr_sched.py:10-28) as data: `adjust_learning_rate(optimizer,
+    data_iter_step / len(data_loader) + epoch, args)` is called at the first iteration of every accumulation group
+    (engine_pretrain.py:87-91), i.e. optimizer step k (1-based) runs at the fractional epoch (k - 1) * epochs_per_step with
+    epochs_per_step = accum_iter / len(data_loader).  Handed to FusedAdamW(schedule=...) the rule is evaluated ON THE DEVICE by
+    oct_adamw_clock_advance, so a captured CUDA graph of the training step keeps following it when replayed."""
+
+    def __init__(self, lr, min_lr, warmup_epochs, epochs, epochs_per_step):
+        assert epochs > warmup_epochs >= 0 and epochs_per_step >= 0
+        self.lr, self.min_lr, self.warmup_epochs, self.epochs = float(lr), float(min_lr), float(warmup_epochs), float(epochs)
+        self.epochs_per_step = float(epochs_per_step)
+
+    def lr_at_step(self, step: int) -> float:
+        """Host-side value of the same rule (logging / tests); step counts from 1."""
+        e = (step - 1) * self.epochs_per_step
+        if e < self.warmup_epochs:
+            return self.lr * e / self.warmup_epochs
+        return self.min_lr + (self.lr - self.min_lr) * 0.5 * (
+            1.0 + math.cos(math.pi * (e - self.warmup_epochs) / (self.epochs - self.warmup_epochs)))
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (decoupled weight decay, bias correction, no amsgrad / maximize), one launch per group.
 
     shadows: optional callable  param -> bf16 tensor of the same shape (or None); the kernel then also writes the bf16 copy
     of the updated weight (MaskedAutoencoderViT keeps such shadows for its tensor-core GEMMs)."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, shadows=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, shadows=None, schedule=None):
+        """schedule: optional CosineSchedule.  With it the step count, the bias corrections and the learning rate live in a
+        16-byte device clock (`self.clock`: int32 step, then lr / bias corrections as fp32) advanced inside step(): the
+        launches of one step() are then replayable from a CUDA graph (a group's `lr` is ignored, its optional `lr_scale`
+        multiplies the scheduled rate; all groups must share betas).  Without it `lr` and the step count are host values
+        baked into the launch — correct eagerly, frozen under graph replay."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._shadows = shadows
+        self.schedule = schedule
+        self.clock = None
         self._tables = {}
         self._norm_ws = None
         self.grad_norm = None
@@ -86,6 +114,34 @@ class FusedAdamW(torch.optim.Optimizer):
         self._tables[gi] = ent
         return ent
 
+    def _norm_workspace(self):
+        tabs = [self._table(gi, g) for gi, g in enumerate(self.param_groups) if g["params"]]
+        tabs = [t for t in tabs if t[2] > 0]
+        if not tabs:
+            return None
+        key = tuple(t[1].data_ptr() for t in tabs)
+        if self._norm_ws is None or self._norm_ws[0] != key:
+            allt = torch.cat([t[1] for t in tabs], 0)
+            self._norm_ws = (key, allt, torch.empty(allt.shape[0], dtype=torch.float32, device=allt.device),
+                             torch.empty(2, dtype=torch.float32, device=allt.device))
+        return self._norm_ws
+
+    @torch.no_grad()
+    def prepare(self, max_grad_norm=None):
+        """Everything step() would otherwise create on first use — the moment buffers, the chunk tables (a host-to-device
+        copy), the gradient-norm workspace and the device clock — built now, without updating anything.  Call it once the
+        gradients sit at their final addresses and BEFORE capturing a step into a CUDA graph: allocations and zero-fills
+        recorded into the graph would be replayed (and the moments reset) on every step."""
+        for gi, g in enumerate(self.param_groups):
+            if g["params"]:
+                self._table(gi, g)
+        if max_grad_norm is not None:
+            self._norm_workspace()
+        if self.schedule is not None and self.clock is None:
+            dev = next(p for g in self.param_groups for p in g["params"]).device
+            self.clock = torch.zeros(4, dtype=torch.int32, device=dev)
+        return self
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0, max_grad_norm=None):
         """grad_scale: multiplied into every gradient first (1 / loss_scale of a GradScaler).  max_grad_norm: clip the global
@@ -100,15 +156,9 @@ class FusedAdamW(torch.optim.Optimizer):
         ops.join_wgrad()  # weight gradients are produced on a side stream (normally already joined at the end of backward)
         clip_ptr = None
         if max_grad_norm is not None:
-            tabs = [self._table(gi, g) for gi, g in enumerate(self.param_groups) if g["params"]]
-            tabs = [t for t in tabs if t[2] > 0]
-            if tabs:
-                key = tuple(t[1].data_ptr() for t in tabs)
-                if self._norm_ws is None or self._norm_ws[0] != key:
-                    allt = torch.cat([t[1] for t in tabs], 0)
-                    self._norm_ws = (key, allt, torch.empty(allt.shape[0], dtype=torch.float32, device=allt.device),
-                                     torch.empty(2, dtype=torch.float32, device=allt.device))
-                _, allt, partial, out = self._norm_ws
+            ws = self._norm_workspace()
+            if ws is not None:
+                _, allt, partial, out = ws
                 rc = lib.oct_grad_norm(ctypes.c_void_p(allt.data_ptr()), allt.shape[0], float(grad_scale), float(max_grad_norm),
                                        ctypes.c_void_p(partial.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                        ctypes.c_void_p(torch.cuda.current_stream(allt.device).cuda_stream))
@@ -116,6 +166,9 @@ class FusedAdamW(torch.optim.Optimizer):
                     raise RuntimeError(f"oct_grad_norm failed (code {rc}): {_lib.last_error()}")
                 self.grad_norm = out[0]
                 clip_ptr = ctypes.c_void_p(out[1:].data_ptr())
+        if self.schedule is not None:
+            self._step_clocked(lib, grad_scale, clip_ptr)
+            return loss
         for gi, group in enumerate(self.param_groups):
             if not group["params"]:
                 continue
@@ -140,3 +193,42 @@ class FusedAdamW(torch.optim.Optimizer):
             # would (the model's bf16 shadow cache and autograd's saved-tensor checks key on them)
             torch._C._autograd._unsafe_set_version_counter(touched, [p._version + 1 for p in touched])
         return loss
+
+    # ------------------------------------------------------------------ graph-replayable path (device clock)
+    def _step_clocked(self, lib, grad_scale, clip_ptr):
+        groups = [(gi, g) for gi, g in enumerate(self.param_groups) if g["params"]]
+        if not groups:
+            return
+        dev = groups[0][1]["params"][0].device
+        betas = {tuple(g["betas"]) for _, g in groups}
+        if len(betas) != 1:
+            raise RuntimeError("FusedAdamW(schedule=...): all parameter groups must share betas (one device clock)")
+        b1, b2 = betas.pop()
+        if self.clock is None:
+            self.clock = torch.zeros(4, dtype=torch.int32, device=dev)
+        sc = self.schedule
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = lib.oct_adamw_clock_advance(ctypes.c_void_p(self.clock.data_ptr()), sc.lr, sc.min_lr, sc.warmup_epochs, sc.epochs,
+                                         sc.epochs_per_step, float(b1), float(b2), st)
+        if rc != 0:
+            raise RuntimeError(f"oct_adamw_clock_advance failed (code {rc}): {_lib.last_error()}")
+        for gi, group in groups:
+            _, table, n = self._table(gi, group)
+            if n == 0:
+                continue
+            rc = lib.oct_adamw_step_clocked(ctypes.c_void_p(table.data_ptr()), n, ctypes.c_void_p(self.clock.data_ptr()),
+                                            float(group.get("lr_scale", 1.0)), float(b1), float(b2), float(group["eps"]),
+                                            float(group["weight_decay"]), float(grad_scale), clip_ptr, st)
+            if rc != 0:
+                raise RuntimeError(f"oct_adamw_step_clocked failed (code {rc}): {_lib.last_error()}")
+            touched = [p for p in group["params"] if p.grad is not None]
+            for p in touched:
+                self.state[p]["step"] += 1  # host mirror: exact for eager steps, the device clock is authoritative under replay
+            torch._C._autograd._unsafe_set_version_counter(touched, [p._version + 1 for p in touched])
+
+    def clock_state(self):
+        """(step, lr) read back from the device clock (synchronises; logging only, engine_pretrain.py:186-187)."""
+        if self.clock is None:
+            return 0, 0.0
+        raw = self.clock.cpu()
+        return int(raw[0]), float(raw[1:2].view(torch.float32)[0])

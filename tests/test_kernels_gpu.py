@@ -438,6 +438,52 @@ def test_fused_adamw_matches_torch():
             assert torch.equal(shadows[id(p)], p.detach().bfloat16())
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_adamw_device_clock_follows_the_cosine_schedule(use_graph):
+    """FusedAdamW(schedule=...): step count, bias corrections and the per-iteration cosine lr (lr_sched.py:10-28) live in a
+    device clock, so REPLAYING one captured optimizer step performs consecutive steps — checked against torch.optim.AdamW
+    driven by the host-side schedule, across warm-up and decay, with a group lr_scale and gradient clipping."""
+    from octcubem_b200 import optim
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(33, 65), torch.nn.LayerNorm(65), torch.nn.Linear(65, 4099)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(33, 65), torch.nn.LayerNorm(65), torch.nn.Linear(65, 4099)).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    sched = optim.CosineSchedule(lr=2e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=4.0, epochs_per_step=0.5)
+    groups, rgroups = optim.add_weight_decay(net, 0.05), optim.add_weight_decay(ref, 0.05)
+    groups[0]["lr_scale"] = rgroups[0]["lr_scale"] = 0.5
+    opt = optim.FusedAdamW(groups, lr=123.0, betas=(0.9, 0.95), schedule=sched)      # the group lr is ignored
+    ropt = torch.optim.AdamW(rgroups, lr=1.0, betas=(0.9, 0.95))
+    grads = [torch.zeros_like(p) for p in net.parameters()]                              # static gradient buffers
+    for p, g in zip(net.parameters(), grads):
+        p.grad = g
+    graph = None
+    for k in range(1, 8):
+        gen = torch.Generator().manual_seed(k)
+        fresh = [torch.randn(p.shape, generator=gen).to(DEV) * 3.0 for p in net.parameters()]
+        for g, f, r in zip(grads, fresh, ref.parameters()):
+            g.copy_(f)
+            r.grad = f.clone()
+        if not use_graph:
+            opt.step(max_grad_norm=1.0)
+        elif graph is None:
+            opt.prepare(max_grad_norm=1.0)                                               # state / tables / clock before capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):                                                # capture does not execute
+                opt.step(max_grad_norm=1.0)
+            graph.replay()
+        else:
+            graph.replay()
+        lr = sched.lr_at_step(k)
+        assert lr == pytest.approx(optim.adjust_learning_rate(ropt, (k - 1) * 0.5, 2e-3, 1e-5, 1.0, 4.0), rel=1e-12)
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        ropt.step()
+        step, dev_lr = opt.clock_state()
+        assert step == k and dev_lr == pytest.approx(lr, rel=1e-6, abs=1e-12)
+        for (name, p), (_, r) in zip(net.named_parameters(), ref.named_parameters()):
+            assert rel(p.detach(), r.detach()) < 2e-6, (k, name)
+
+
 def test_fused_adamw_grad_scale_and_errors():
     from octcubem_b200 import optim
     p = torch.nn.Parameter(torch.randn(1000, device=DEV))

@@ -47,3 +47,14 @@ def test_fused_adamw_refuses_cpu_parameters():
     p.grad = torch.randn(4)
     with pytest.raises(RuntimeError):
         optim.FusedAdamW([p]).step()
+
+
+def test_cosine_schedule_object_equals_adjust_learning_rate():
+    """CosineSchedule.lr_at_step(k) = the reference rule at the first iteration of accumulation group k (engine_pretrain.py:87-91)."""
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    accum, iters_per_epoch = 4, 250
+    s = optim.CosineSchedule(lr=1.6e-3, min_lr=1e-6, warmup_epochs=5, epochs=100, epochs_per_step=accum / iters_per_epoch)
+    for k in (1, 2, 63, 313, 314, 5000, 6250):
+        data_iter_step = (k - 1) * accum
+        want = optim.adjust_learning_rate(opt, data_iter_step / iters_per_epoch, 1.6e-3, 1e-6, 5, 100)
+        assert s.lr_at_step(k) == pytest.approx(want, rel=1e-9, abs=1e-15)
