@@ -100,7 +100,7 @@ class GradReducer:
         from . import ops
         for b in self.buckets:
             for p, v in zip(b.params, b.views):
-                ops.grad_sinks[p.data_ptr()] = v
+                ops.grad_sinks[p.data_ptr()] = (v, p)
                 self._sink_keys.append(p.data_ptr())
 
     def _clear_sinks(self):
@@ -159,6 +159,7 @@ class GradReducer:
     def finish(self):
         """Call after loss.backward(): joins the communication stream; on the discovery step performs the (non-overlapped)
         reduction and builds the buckets for the following steps."""
+        discovery = self._discovering
         if self._discovering:
             self._build(self._order)
             self._discovering = False
@@ -178,6 +179,14 @@ class GradReducer:
                     if not self._prescaled:
                         b.flat.mul_(1.0 / self.world)
                     b.work = None
+        if self.world > 1 and not discovery and any(b.pending != 0 for b in self.buckets):
+            # a gradient that never reached its hook: e.g. a second backward() into gradients that were not cleared — the
+            # in-place weight-gradient sinks then accumulate without telling autograd, and this bucket was never reduced
+            stuck = [n for b in self.buckets if b.pending != 0 for n in b.names][:4]
+            for b in self.buckets:
+                b.pending = len(b.params)
+            raise RuntimeError("GradReducer.finish(): some buckets were not reduced on this step (gradient accumulation over "
+                               f"several backward passes is only supported at world size 1); first parameters: {stuck}")
         for b in self.buckets:
             b.pending = len(b.params)
         self._prescaled = False
@@ -185,6 +194,9 @@ class GradReducer:
     def zero_grad(self):
         """Keeps param.grad pointing into the buckets (so the next hooks need no copy when autograd accumulates in place)
         and zeroes them; equivalent to optimizer.zero_grad(set_to_none=False)."""
+        if self.device.type == "cuda":
+            from . import ops
+            ops._sinks_pass_done()  # (a backward pass that died half-way never ran its end-of-pass callback)
         if self.buckets is None:
             self.model.zero_grad(set_to_none=True)
             return

@@ -110,16 +110,38 @@ def gemm(layout, A, B, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, aux=Non
     return out
 
 
-# parameter storage pointer -> fp32 tensor that should receive that parameter's gradient (dp.GradReducer registers the views
-# of its flat all-reduce buckets here, so that weight gradients are produced in place instead of being copied there)
+# parameter storage pointer -> (fp32 tensor that should receive that parameter's gradient, the parameter).  dp.GradReducer
+# registers the views of its flat all-reduce buckets here, so that weight gradients are produced in place instead of being
+# copied there.
 grad_sinks = {}
+_sinks_written = set()      # sinks already written during the running backward pass
+_sinks_cb_queued = [False]
+
+
+def _sinks_pass_done():
+    _sinks_written.clear()
+    _sinks_cb_queued[0] = False
 
 
 def _sink(ptr, shape):
-    """A FRESH alias of the registered sink (autograd's AccumulateGrad adopts a gradient without copying only when nobody
-    else holds a reference to the very tensor object it is handed)."""
-    v = grad_sinks.get(ptr)
-    return None if v is None else v.view(shape)
+    """-> (destination or None, beta, hand_back).
+    First write of a backward pass into an empty sink: beta = 0 and a FRESH alias of the sink is handed to autograd
+    (AccumulateGrad adopts a gradient without copying only when nobody else holds a reference to that tensor object).
+    If the sink already holds live gradient — the weight was used twice in this pass (the joint step runs a 3D and a 2D
+    forward through the same blocks before one backward, engine_pretrain.py:117-149), or `param.grad` still points into the
+    bucket from an earlier micro-step of a gradient-accumulation group — the kernel accumulates into it (beta = 1) and autograd
+    gets None for this use: handing it a second alias of the same memory would make it add the buffer to itself."""
+    ent = grad_sinks.get(ptr)
+    if ent is None:
+        return None, 0, True
+    view, param = ent
+    g = param.grad
+    live = ptr in _sinks_written or (g is not None and g.data_ptr() == view.data_ptr())
+    _sinks_written.add(ptr)
+    if not _sinks_cb_queued[0]:
+        _sinks_cb_queued[0] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_sinks_pass_done)
+    return view.view(shape), (1 if live else 0), not live
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -157,10 +179,10 @@ def join_wgrad(device=None):
             torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(_wgrad_streams[idx])
 
 
-def wgrad_bias_async(dy2, x2, dw=None, db=None):
+def wgrad_bias_async(dy2, x2, dw=None, db=None, beta=0):
     """wgrad_bias on the side stream (inside a backward pass, bf16 path); falls back to the current stream otherwise."""
     if not overlap_wgrad or dy2.dtype != torch.bfloat16:
-        return wgrad_bias(dy2, x2, dw, db)
+        return wgrad_bias(dy2, x2, dw, db, beta)
     dev = dy2.device
     side, cur = wgrad_stream(dev), torch.cuda.current_stream(dev)
     # one join callback per call (the first to run does the work): a backward pass that died half-way leaves the flag set,
@@ -169,28 +191,29 @@ def wgrad_bias_async(dy2, x2, dw=None, db=None):
     torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad(dev))
     side.wait_stream(cur)  # dy2 / x2 are complete on the current stream
     with torch.cuda.stream(side):
-        out = wgrad_bias(dy2, x2, dw, db)
+        out = wgrad_bias(dy2, x2, dw, db, beta)
     # the operands were allocated on the current stream: the caching allocator must not recycle them under the side stream
     dy2.record_stream(side)
     x2.record_stream(side)
     return out
 
 
-def wgrad_bias(dy2, x2, dw=None, db=None):
-    """(dW [n_out, k_in], db [n_out]) = (dy2^T x2, column sums of dy2), both fp32.  bf16 operands: ONE tcgen05 kernel
-    (oct_gemm_wgrad_bias: the bias gradient rides on the wgrad GEMM as an extra MMA against a tile of ones); fp32 parity
-    mode: CUDA-core GEMM + the deterministic two-stage column sum.  dw / db: optional destinations (see grad_sinks)."""
+def wgrad_bias(dy2, x2, dw=None, db=None, beta=0):
+    """(dW [n_out, k_in], db [n_out]) (= or, beta = 1, +=) (dy2^T x2, column sums of dy2), both fp32.  bf16 operands: ONE
+    tcgen05 kernel (oct_gemm_wgrad_bias: the bias gradient rides on the wgrad GEMM as an extra MMA against a tile of ones);
+    fp32 parity mode: CUDA-core GEMM + the deterministic two-stage column sum.  dw / db: optional destinations (grad_sinks)."""
     _chk(dy2, x2, dw, db)
+    assert beta == 0 or (dw is not None and db is not None)
     tokens, n_out = dy2.shape
     k_in = x2.shape[1]
     if dy2.dtype != torch.bfloat16:
-        return gemm(GEMM_TN, dy2, x2, n_out, k_in, tokens, torch.float32, out=dw), colsum(dy2, out=db)
+        return gemm(GEMM_TN, dy2, x2, n_out, k_in, tokens, torch.float32, out=dw, beta=beta), colsum(dy2, out=db, beta=beta)
     if dw is None:
         dw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy2.device)
     if db is None:
         db = torch.empty(n_out, dtype=torch.float32, device=dy2.device)
     _call("oct_gemm_wgrad_bias", OCT_BF16, _p(dy2), _p(x2), _p(dw), _p(db), n_out, k_in, tokens, dy2.stride(0), x2.stride(0),
-          dw.stride(0), 0, _stream())
+          dw.stride(0), beta, _stream())
     return dw, db
 
 
@@ -275,6 +298,17 @@ def cast_bf16(src_f32, dst_bf16=None):
     return dst_bf16
 
 
+def _wgrad_into_sinks(dy2, x2, w_sink, b_sink):
+    """Weight + bias gradient of one nn.Linear, produced in the reducer's buckets when they are registered (see _sink)."""
+    dw, beta_w, give_w = _sink(*w_sink)
+    db, beta_b, give_b = _sink(*b_sink)
+    if beta_w != beta_b or (dw is None) != (db is None):  # the pair always travels together; be safe if it ever does not
+        dw2, db2 = wgrad_bias_async(dy2, x2)
+        return dw2, db2
+    dw, db = wgrad_bias_async(dy2, x2, dw, db, beta_w)
+    return (dw if give_w else None), (db if give_b else None)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # autograd Functions
 # ----------------------------------------------------------------------------------------------------------------
@@ -306,7 +340,7 @@ class LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:  # first: it forks onto the wgrad stream and overlaps the dgrad
             wp, ws_, bp, bs = ctx.sinks
-            dw, db = wgrad_bias_async(dy2, x2, _sink(wp, ws_), _sink(bp, bs))
+            dw, db = _wgrad_into_sinks(dy2, x2, (wp, ws_), (bp, bs))
         elif ctx.needs_input_grad[1]:
             dw = gemm(GEMM_TN, dy2, x2, N, K, M, torch.float32)
         elif ctx.needs_input_grad[2]:
@@ -345,9 +379,9 @@ class MlpFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         M = x2.shape[0]
         (w1s, b1s, w2s, b2s) = ctx.sinks
-        dw2, db2 = wgrad_bias_async(dy2, act, _sink(*w2s), _sink(*b2s))  # forks onto the wgrad stream: overlaps the dgrad chain
+        dw2, db2 = _wgrad_into_sinks(dy2, act, w2s, b2s)  # forks onto the wgrad stream: overlaps the dgrad chain
         dpre = gemm(GEMM_NN, dy2, wb, M, hid, out_dim, x2.dtype, EPI_DGELU, aux=pre)
-        dw1, db1 = wgrad_bias_async(dpre, x2, _sink(*w1s), _sink(*b1s))
+        dw1, db1 = _wgrad_into_sinks(dpre, x2, w1s, b1s)
         dx = gemm(GEMM_NN, dpre, wa, M, dim, hid, x2.dtype).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         return dx, dw1, db1, dw2, db2, None, None
 

@@ -106,6 +106,44 @@ def test_joint_3d_plus_2d_step_vs_oracle(precision, tol):
         assert rel(got[k], want[k]) < (tol if precision == "fp32" else 5e-2), k   # per-tensor bound of the toy-step test
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_joint_step_through_the_reducer_sinks(precision, tol):
+    """The same joint step with a GradReducer (world size 1): after its discovery step the Linear / Mlp weight gradients are
+    written by the wgrad kernels straight into the bucket views (ops.grad_sinks).  Every block weight is used TWICE in this
+    backward pass (3D + 2D forward): the second use must accumulate into the sink, not overwrite it.  A second backward
+    without zero_grad (gradient accumulation) must then double the gradients."""
+    from octcubem_b200.dp import GradReducer
+    sd, vol3, noise3 = toy_inputs()
+    vol2 = O.synthetic_volume(2, 3, 128, 128, seed=3, zero_pad_frames=0)
+    noise2 = O.synthetic_noise(2, 64, seed=6)
+    (_, g3) = O.forward_backward(TOY, sd, vol3, 0.9, noise3)
+    (_, g2) = O.forward_backward(TOY, sd, vol2, 0.75, noise2)
+    want = {k: g3.get(k, 0) + g2.get(k, 0) for k in set(g3) | set(g2)}
+    m = build(TOY, sd, precision)
+    reducer = GradReducer(m)
+    try:
+        def step():
+            loss3, _, _ = m(vol3.to(DEV), mask_ratio=0.9, noise=noise3.to(DEV))
+            loss2, _, _ = m(vol2.to(DEV), mask_ratio=0.75, noise=noise2.to(DEV))
+            reducer.backward(loss3 + loss2)
+            reducer.finish()
+        reducer.zero_grad()
+        step()                                   # discovery: plain autograd gradients, buckets built afterwards
+        reducer.zero_grad()
+        step()                                   # gradients land in the sinks
+        from octcubem_b200 import ops
+        w = m.blocks[0].mlp.fc1.weight
+        assert w.grad.data_ptr() == ops.grad_sinks[w.data_ptr()][0].data_ptr()       # produced in place
+        got = {k: p.grad.clone() for k, p in m.named_parameters()}
+        for k in got:
+            assert rel(got[k], want[k]) < (tol if precision == "fp32" else 5e-2), k
+        step()                                   # no zero_grad: accumulate
+        for k, p in m.named_parameters():
+            assert rel(p.grad, 2 * got[k]) < (1e-5 if precision == "fp32" else 2e-2), k
+    finally:
+        reducer.remove()
+
+
 def test_module_surface_and_methods():
     sd, vol, noise = toy_inputs()
     m = build(TOY, sd, "fp32")

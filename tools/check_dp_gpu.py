@@ -53,7 +53,7 @@ for step in range(3):  # step 0 = discovery (non-overlapped), then the hooked / 
         worst = max(worst, err)
         assert err < 2e-3, (step, k, err)  # same bf16 kernels on both sides; only the split-K / reduction order differs
 in_place = sum(1 for k, p in model.named_parameters() if p.grad is not None and p.data_ptr() in ops.grad_sinks
-               and p.grad.data_ptr() == ops.grad_sinks[p.data_ptr()].data_ptr())
+               and p.grad.data_ptr() == ops.grad_sinks[p.data_ptr()][0].data_ptr())
 print(f"rank {rank}: OK, worst rel err {worst:.2e}, {in_place} gradients live in their buckets, {len(red.buckets)} buckets", flush=True)
 dist.barrier()
 dist.destroy_process_group()
