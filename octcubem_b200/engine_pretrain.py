@@ -1,0 +1,159 @@
+"""The optimizer step of the reference's training loop as ONE replayable CUDA graph.
+
+Mirrors the loop body of `train_one_epoch_joint` (Pre-training/engine_pretrain.py:83-161) — the caller on the input side of
+the hot path:
+    lr_sched.adjust_learning_rate(...)                              :87-91   -> device clock of optim.FusedAdamW
+    samples.reshape(b * r, c, t, h, w)                              :101-103
+    feat = forward_patch_embed(samples); misc.get_mask(feat)        :112-115 -> dropped: `forward` discards pre_mask
+                                                                                (models...:677, quirk Q7), the pass is dead
+    loss, _, _ = model(samples, mask_ratio, frame_loss=True, ...)   :117-122
+    loss_2d, _, _ = model(sample_2d, mask_ratio=mask_ratio_2d)      :124-127
+    loss = loss + loss_2d; loss /= accum_iter                       :148-163
+    loss_scaler(loss, optimizer, clip_grad=..., update_grad=...)    :164-170 -> backward, grad-norm clip, AdamW
+    optimizer.zero_grad()                                           :172-173
+    loss.item() x3, frame_loss.item() per frame, cuda.synchronize() :130-147,175 -> no host sync inside the step: results
+                                                                                stay on the device until the caller reads them
+The first `warm_steps` calls with a new input signature run eagerly (they are real training steps: lazy initialisation,
+the reducer's bucket discovery); the next call captures the whole step — both forwards, backward, the gradient all-reduce,
+the device-side grad-norm clip and the AdamW update — and from then on the step is one graph launch.  Input signatures
+(volume shape, 2D batch shape, the 2D keep count that `mask_ratio_2d_scheduler` changes from epoch to epoch) each get their
+own graph.  bf16 needs no loss scaling, so NativeScaler's GradScaler is not reproduced; its clip_grad / grad-norm output is.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from .dp import GradReducer
+from .models_mae import len_keep_of
+from .optim import FusedAdamW
+
+
+def K_scheduler(epoch, K_max=0.7, K_min=0.3, all_epoch=100, warmup_epochs=10, epoch_offset=0):
+    """main_pretrain_oph_joint_2d512_flash_attn.py:53-59: starts at K_max, decreases linearly to K_min after the warm-up."""
+    n = epoch - epoch_offset
+    if n <= warmup_epochs:
+        return K_max
+    return K_max - (n - warmup_epochs) * (K_max - K_min) / (all_epoch - warmup_epochs - epoch_offset)
+
+
+def mask_ratio_2d_scheduler(epoch, mask_ratio_max=0.85, mask_ratio_min=0.75, all_epoch=100, warmup_epochs=10, epoch_offset=0):
+    """main_pretrain_oph_joint_2d512_flash_attn.py:61-67: starts at mask_ratio_min, increases linearly to mask_ratio_max."""
+    n = epoch - epoch_offset
+    if n <= warmup_epochs:
+        return mask_ratio_min
+    return mask_ratio_min + (n - warmup_epochs) * (mask_ratio_max - mask_ratio_min) / (all_epoch - warmup_epochs - epoch_offset)
+
+
+class StepResult:
+    """Device-resident results of one step (nothing has been copied to the host yet)."""
+
+    def __init__(self, loss, loss_2d, loss_all, frame_loss, grad_norm):
+        self.loss, self.loss_2d, self.loss_all, self.frame_loss, self.grad_norm = loss, loss_2d, loss_all, frame_loss, grad_norm
+
+    def check_finite(self) -> Dict[str, float]:
+        """The reference's per-iteration host read (engine_pretrain.py:130-161): returns the python floats and raises like
+        `raise Exception("Loss is {}, stopping training")` when the 3D loss is not finite.  Synchronises."""
+        out = {"loss": float(self.loss), "loss_all": float(self.loss_all)}
+        if self.loss_2d is not None:
+            out["loss_2d"] = float(self.loss_2d)
+        if self.grad_norm is not None:
+            out["grad_norm"] = float(self.grad_norm)
+        if not math.isfinite(out["loss"]):
+            raise Exception("Loss is {}, stopping training".format(out["loss"]))
+        return out
+
+
+class JointPretrainStep:
+    def __init__(self, model, optimizer: FusedAdamW, mask_ratio: float = 0.9, clip_grad: Optional[float] = None,
+                 accum_iter: int = 1, use_graph: bool = True, warm_steps: int = 2, process_group=None):
+        if accum_iter != 1:
+            raise NotImplementedError("JointPretrainStep: accum_iter > 1 is not implemented (the reference recipe uses 1 per GPU batch)")
+        if use_graph and optimizer.schedule is None:
+            raise ValueError("JointPretrainStep(use_graph=True) needs FusedAdamW(schedule=CosineSchedule(...)): a host-side "
+                             "learning rate / step count would be frozen into the captured graph")
+        self.model, self.optimizer = model, optimizer
+        self.mask_ratio, self.clip_grad = mask_ratio, clip_grad
+        self.use_graph, self.warm_steps = use_graph, max(2, int(warm_steps))  # bucket discovery + one bucketed step
+        self.reducer = GradReducer(model, process_group)
+        self._entries: Dict[tuple, dict] = {}
+        self._joint: Optional[bool] = None
+
+    # ------------------------------------------------------------------ one step, eager or under capture
+    def _run(self, vol, img, ratio_2d, noise, noise_2d, out):
+        self.reducer.zero_grad()
+        (loss, frame_loss), _, _ = self.model(vol, mask_ratio=self.mask_ratio, frame_loss=True, noise=noise)
+        total = loss
+        if img is not None:
+            loss_2d, _, _ = self.model(img, mask_ratio=ratio_2d, noise=noise_2d)
+            total = loss + loss_2d
+            out["loss_2d"].copy_(loss_2d.detach())
+        self.reducer.backward(total)
+        self.reducer.finish()
+        self.optimizer.step(max_grad_norm=self.clip_grad)
+        self.model.shadows_current()
+        out["loss"].copy_(loss.detach())
+        out["loss_all"].copy_(total.detach())
+        out["frame_loss"].copy_(frame_loss)
+        if self.clip_grad is not None and self.optimizer.grad_norm is not None:
+            out["grad_norm"].copy_(self.optimizer.grad_norm)
+
+    def _result(self, out, joint):
+        return StepResult(out["loss"], out["loss_2d"] if joint else None, out["loss_all"], out["frame_loss"],
+                          out["grad_norm"] if self.clip_grad is not None else None)
+
+    def __call__(self, samples, sample_2d=None, mask_ratio_2d: float = 0.75, noise=None, noise_2d=None) -> StepResult:
+        """samples [b,c,t,h,w] or [b,r,c,t,h,w] (engine_pretrain.py:101-103), sample_2d [b2,1,3,H,W] or None, both already on
+        the device.  `noise` / `noise_2d` (optional) replace the models' torch.rand draws for reproducible masks."""
+        if samples.dim() == 6:
+            b, r, c, t, h, w = samples.shape
+            samples = samples.reshape(b * r, c, t, h, w)
+        joint = sample_2d is not None
+        if self._joint is not None and joint != self._joint:
+            # another set of parameters takes part (quirk Q13): rebuild the buckets, forget graphs that point into the old ones
+            self.reducer.reset()
+            self._entries.clear()
+        self._joint = joint
+        dev = samples.device
+        pe = self.model.high_res_patch_embed if joint else None
+        keep_2d = len_keep_of(pe.input_size[1] * pe.input_size[2], mask_ratio_2d) if joint else None
+        key = (tuple(samples.shape), tuple(sample_2d.shape) if joint else None, keep_2d, noise is not None, noise_2d is not None)
+        ent = self._entries.get(key)
+        if ent is None:
+            tp = samples.shape[2] // self.model.patch_embed.t_patch_size
+            out = {"loss": torch.zeros((), device=dev), "loss_2d": torch.zeros((), device=dev),
+                   "loss_all": torch.zeros((), device=dev), "frame_loss": torch.zeros(samples.shape[0], tp, device=dev),
+                   "grad_norm": torch.zeros((), device=dev)}
+            ent = self._entries[key] = {"calls": 0, "graph": None, "out": out}
+        out = ent["out"]
+        if not self.use_graph or ent["calls"] < self.warm_steps:
+            ent["calls"] += 1
+            self._run(samples, sample_2d, mask_ratio_2d, noise, noise_2d, out)
+            return self._result(out, joint)
+        if ent["graph"] is None:
+            st = ent["static"] = {"vol": samples.clone(), "img": sample_2d.clone() if joint else None,
+                                  "noise": noise.clone() if noise is not None else None,
+                                  "noise_2d": noise_2d.clone() if noise_2d is not None else None}
+            self.optimizer.prepare(max_grad_norm=self.clip_grad)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):  # capture records, it does not execute
+                self._run(st["vol"], st["img"], mask_ratio_2d, st["noise"], st["noise_2d"], out)
+            ent["graph"] = graph
+        else:
+            st = ent["static"]
+            st["vol"].copy_(samples, non_blocking=True)
+            if joint:
+                st["img"].copy_(sample_2d, non_blocking=True)
+            if noise is not None:
+                st["noise"].copy_(noise, non_blocking=True)
+            if noise_2d is not None:
+                st["noise_2d"].copy_(noise_2d, non_blocking=True)
+        ent["graph"].replay()
+        return self._result(out, joint)
+
+    def close(self):
+        self._entries.clear()
+        self.reducer.remove()

@@ -1,0 +1,78 @@
+"""GPU: the graph-replayed training step (octcubem_b200/engine_pretrain.JointPretrainStep, mirror of the loop body of
+Pre-training/engine_pretrain.py:83-161) against a plain eager loop (autograd + torch.optim.AdamW + clip_grad_norm_ + the
+host-side cosine schedule of lr_sched.py) on the same module, inputs and masks."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from octcubem_b200 import models_mae, optim  # noqa: E402
+from octcubem_b200.engine_pretrain import JointPretrainStep  # noqa: E402
+from oracle import mae3d_oracle as O  # noqa: E402
+from oracle.gen_golden import TOY, toy_inputs  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(sd, precision):
+    m = models_mae.MaskedAutoencoderViT(**TOY.ref_kwargs(), use_flash_attn=True, precision=precision,
+                                        norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).to(DEV)
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+@pytest.mark.parametrize("joint", [True, False])
+def test_graph_replayed_steps_match_an_eager_torch_loop(joint):
+    sd, _, _ = toy_inputs()
+    sched = dict(lr=3e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=5.0)
+    eng_model, ref_model = build(sd, "fp32"), build(sd, "fp32")
+    opt = optim.FusedAdamW(optim.add_weight_decay(eng_model, 0.05), betas=(0.9, 0.95),
+                           schedule=optim.CosineSchedule(**sched, epochs_per_step=0.5))
+    engine = JointPretrainStep(eng_model, opt, mask_ratio=0.9, clip_grad=0.5, use_graph=True, warm_steps=2)
+    ropt = torch.optim.AdamW(optim.add_weight_decay(ref_model, 0.05), lr=1.0, betas=(0.9, 0.95))
+    try:
+        for k in range(1, 7):                                   # steps 1-2 eager, 3 captures + replays, 4-6 replay
+            vol = O.synthetic_volume(2, 12, 64, 64, seed=10 + k, zero_pad_frames=1).to(DEV)
+            noise = O.synthetic_noise(2, 64, seed=20 + k).to(DEV)
+            img = O.synthetic_volume(2, 3, 128, 128, seed=30 + k, zero_pad_frames=0).to(DEV) if joint else None
+            noise2 = O.synthetic_noise(2, 64, seed=40 + k).to(DEV) if joint else None
+            res = engine(vol.view(1, 2, 1, 12, 64, 64), img, mask_ratio_2d=0.75, noise=noise, noise_2d=noise2)
+            # the eager reference loop (engine_pretrain.py:87-173 with torch's optimizer)
+            optim.adjust_learning_rate(ropt, (k - 1) * 0.5, sched["lr"], sched["min_lr"], sched["warmup_epochs"], sched["epochs"])
+            ref_model.zero_grad(set_to_none=True)
+            (loss, fl), _, _ = ref_model(vol, mask_ratio=0.9, frame_loss=True, noise=noise)
+            total = loss
+            if joint:
+                loss2, _, _ = ref_model(img, mask_ratio=0.75, noise=noise2)
+                total = loss + loss2
+            total.backward()
+            norm = torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.5)
+            ropt.step()
+            got = res.check_finite()
+            assert got["loss"] == pytest.approx(float(loss), rel=2e-5), k
+            assert got["loss_all"] == pytest.approx(float(total), rel=2e-5), k
+            assert got["grad_norm"] == pytest.approx(float(norm), rel=1e-4), k
+            assert rel(res.frame_loss, fl) < 2e-5
+            if joint:
+                assert got["loss_2d"] == pytest.approx(float(loss2), rel=2e-5), k
+            for (name, p), (_, r) in zip(eng_model.named_parameters(), ref_model.named_parameters()):
+                assert rel(p.detach(), r.detach()) < 2e-5, (k, name)
+        assert opt.clock_state()[0] == 6
+        ent = next(iter(engine._entries.values()))
+        assert ent["graph"] is not None and ent["calls"] == 2
+    finally:
+        engine.close()
+
+
+def test_engine_refuses_a_host_side_schedule_under_graphs():
+    sd, _, _ = toy_inputs()
+    m = build(sd, "fp32")
+    with pytest.raises(ValueError, match="schedule"):
+        JointPretrainStep(m, optim.FusedAdamW(optim.add_weight_decay(m, 0.05)), use_graph=True)
+    with pytest.raises(NotImplementedError):
+        JointPretrainStep(m, optim.FusedAdamW(optim.add_weight_decay(m, 0.05)), use_graph=False, accum_iter=2)

@@ -58,3 +58,13 @@ def test_cosine_schedule_object_equals_adjust_learning_rate():
         data_iter_step = (k - 1) * accum
         want = optim.adjust_learning_rate(opt, data_iter_step / iters_per_epoch, 1.6e-3, 1e-6, 5, 100)
         assert s.lr_at_step(k) == pytest.approx(want, rel=1e-9, abs=1e-15)
+
+
+def test_mask_ratio_and_K_schedulers():
+    """main_pretrain_oph_joint_2d512_flash_attn.py:53-67: flat during the warm-up, then linear."""
+    from octcubem_b200.engine_pretrain import K_scheduler, mask_ratio_2d_scheduler
+    assert mask_ratio_2d_scheduler(0) == 0.75 and mask_ratio_2d_scheduler(10) == 0.75
+    assert mask_ratio_2d_scheduler(55) == pytest.approx(0.75 + 45 * 0.10 / 90)
+    assert mask_ratio_2d_scheduler(100) == pytest.approx(0.85)
+    assert mask_ratio_2d_scheduler(30, epoch_offset=20, all_epoch=120) == 0.75
+    assert K_scheduler(5) == 0.7 and K_scheduler(100) == pytest.approx(0.3) and K_scheduler(55) == pytest.approx(0.5)
