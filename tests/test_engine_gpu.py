@@ -29,7 +29,7 @@ def build(sd, precision):
 @pytest.mark.parametrize("joint", [True, False])
 def test_graph_replayed_steps_match_an_eager_torch_loop(joint):
     sd, _, _ = toy_inputs()
-    sched = dict(lr=3e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=5.0)
+    sched = dict(lr=3e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=3.0)   # lr per step: 0, 1.5e-3, 3e-3, 2.6e-3, 1.5e-3, 4.5e-4
     eng_model, ref_model = build(sd, "fp32"), build(sd, "fp32")
     opt = optim.FusedAdamW(optim.add_weight_decay(eng_model, 0.05), betas=(0.9, 0.95),
                            schedule=optim.CosineSchedule(**sched, epochs_per_step=0.5))
@@ -54,15 +54,19 @@ def test_graph_replayed_steps_match_an_eager_torch_loop(joint):
             norm = torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.5)
             ropt.step()
             got = res.check_finite()
-            assert got["loss"] == pytest.approx(float(loss), rel=2e-5), k
-            assert got["loss_all"] == pytest.approx(float(total), rel=2e-5), k
-            assert got["grad_norm"] == pytest.approx(float(norm), rel=1e-4), k
-            assert rel(res.frame_loss, fl) < 2e-5
+            # Adam divides by sqrt(v): round-off level differences between the two gradient paths (in-place sinks with atomics
+            # vs autograd sums) are amplified for near-zero entries, so parameters agree to ~1e-4, not to fp32 round-off; a
+            # learning rate or bias correction frozen at capture time (step 3) would be off by 10 % and more from step 4 on
+            assert got["loss"] == pytest.approx(float(loss.detach()), rel=2e-4), k
+            assert got["loss_all"] == pytest.approx(float(total), rel=2e-4), k
+            assert got["grad_norm"] == pytest.approx(float(norm), rel=1e-3), k
+            assert rel(res.frame_loss, fl.detach()) < 2e-4
             if joint:
-                assert got["loss_2d"] == pytest.approx(float(loss2), rel=2e-5), k
+                assert got["loss_2d"] == pytest.approx(float(loss2), rel=2e-4), k
             for (name, p), (_, r) in zip(eng_model.named_parameters(), ref_model.named_parameters()):
-                assert rel(p.detach(), r.detach()) < 2e-5, (k, name)
-        assert opt.clock_state()[0] == 6
+                assert rel(p.detach(), r.detach()) < 1e-3, (k, name)
+        step, dev_lr = opt.clock_state()
+        assert step == 6 and dev_lr == pytest.approx(opt.schedule.lr_at_step(6), rel=1e-5)
         ent = next(iter(engine._entries.values()))
         assert ent["graph"] is not None and ent["calls"] == 2
     finally:
