@@ -1,8 +1,9 @@
-"""Joint 2D-512 + 3D step (BASELINE cfg-4): what engine_pretrain.py:109-149 does per optimizer step —
-forward_patch_embed (the engine's extra Conv3d pass), a 3D forward (frame_loss=True), a 2D-512 forward at its own mask
-ratio, `loss = loss + loss_2d`, one backward — plus the fused AdamW update.  Prints one JSON line (informational; the
-headline bench stays bench.py / cfg-2).
-    python tools/bench_joint.py [--b3d 2] [--b2d 16] [--frames 60] [--steps 10]
+"""Joint 2D-512 + 3D step (BASELINE cfg-4): what engine_pretrain.py:83-173 does per optimizer step — a 3D
+forward (frame_loss=True), a 2D-512 forward at its own mask ratio, `loss = loss + loss_2d`, one backward, grad-norm clip,
+AdamW on the per-iteration cosine schedule — through octcubem_b200.engine_pretrain.JointPretrainStep (two eager steps,
+then ONE CUDA graph per input signature; learning rate / step count live in the optimizer's device clock).
+Prints one JSON line (informational; the headline bench stays bench.py / cfg-2).
+    python tools/bench_joint.py [--b3d 2] [--b2d 16] [--frames 60] [--steps 10] [--no-graph]
 """
 import argparse
 import json
@@ -13,7 +14,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from octcubem_b200 import models_mae, optim  # noqa: E402
-from octcubem_b200.dp import GradReducer  # noqa: E402
+from octcubem_b200.engine_pretrain import JointPretrainStep  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--b3d", type=int, default=2)
@@ -30,54 +31,27 @@ model = models_mae.flash_attn_mae_vit_large_patch16(
     high_res_input_size=512, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16, precision="bf16").to(dev)
 vol = torch.rand(a.b3d, 1, a.frames, 256, 256, device=dev)
 img = torch.rand(a.b2d, 1, 3, 512, 512, device=dev)
-opt = optim.FusedAdamW(optim.add_weight_decay(model, 0.05), lr=1e-6, betas=(0.9, 0.95), shadows=model.shadow_of)
-# world size 1: the reducer only pins every gradient to a fixed address (its flat buckets), which is what lets the whole
-# step — optimizer table included — be captured into one CUDA graph
-reducer = GradReducer(model)
-total_out = torch.zeros((), device=dev)
+sched = optim.CosineSchedule(lr=1.6e-3, min_lr=1e-6, warmup_epochs=5, epochs=100, epochs_per_step=1.0 / 2000)
+opt = optim.FusedAdamW(optim.add_weight_decay(model, 0.05), betas=(0.9, 0.95), shadows=model.shadow_of, schedule=sched)
+engine = JointPretrainStep(model, opt, mask_ratio=0.9, clip_grad=1.0, use_graph=not a.no_graph, warm_steps=3)
 
-
-def step():
-    reducer.zero_grad()
-    feat = model.forward_patch_embed(vol).detach()             # engine_pretrain.py:112 (feeds the dead get_mask pass)
-    (loss, frame_loss), _, _ = model(vol, mask_ratio=0.9, frame_loss=True)
-    loss_2d, _, _ = model(img, mask_ratio=a.mask2d)
-    total = loss + loss_2d
-    total.backward()
-    reducer.finish()
-    opt.step(max_grad_norm=1.0)
-    model.shadows_current()
-    total_out.copy_(total.detach())
-    return feat
-
-
-for _ in range(3):
-    step()
+for _ in range(5):                      # 3 eager steps, capture + first replay, one more replay
+    res = engine(vol, img, mask_ratio_2d=a.mask2d)
 torch.cuda.synchronize()
 unused = sorted(k for k, p in model.named_parameters() if p.grad is None)
-graph = None
-if not a.no_graph:
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        step()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        step()
-    graph.replay()
-    torch.cuda.synchronize()
-run = graph.replay if graph is not None else step
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(a.steps):
-    run()
+    res = engine(vol, img, mask_ratio_2d=a.mask2d)
 e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / a.steps
-total = total_out
+vals = res.check_finite()
+step, lr = opt.clock_state()
+graphed = any(ent["graph"] is not None for ent in engine._entries.values())
 print(json.dumps({"workload": f"joint step: {a.b3d} x {a.frames}x256x256 volumes @0.9 + {a.b2d} x 3x512x512 en-face triplets @{a.mask2d}, "
-                              "bf16 fwd+bwd + grad-norm clip + fused AdamW, " + ("one CUDA graph" if graph is not None else "eager"),
+                              "bf16 fwd+bwd + grad-norm clip + fused AdamW on the device-clock cosine schedule, "
+                              + ("one CUDA graph, inputs copied into its static buffers every step" if graphed else "eager"),
                   "ms_per_step": ms, "volumes_per_s": a.b3d / (ms / 1e3), "images_2d_per_s": a.b2d / (ms / 1e3),
-                  "loss": float(total), "finite": bool(torch.isfinite(total)), "params_without_grad": unused}))
+                  "loss_all": vals["loss_all"], "grad_norm": vals.get("grad_norm"), "optimizer_steps": step, "lr": lr,
+                  "lr_expected": sched.lr_at_step(step), "params_without_grad": unused}))
