@@ -187,6 +187,14 @@ int oct_mean_pool_fwd(const void* x, int x_dtype, void* out, int out_dtype, int6
 int oct_mean_pool_bwd(const void* dout, int dout_dtype, void* dx, int dx_dtype, int64_t B, int64_t S, int64_t C, int64_t row0,
                       int64_t row1, oct_stream_t stream);
 
+/* ---- volume ingest: uint8 cube -> the step's fp32 input, replacing the loader's CPU work ------------------
+ * dst [B,1,T,H,W] f32 <- src [B,T_src,H,W] u8 : value / divisor (ToTensor's /255, PatientDataset_inhouse.py:420), centre
+ * zero-padding ((T - T_src) // 2 frames on the left) or centre cropping (frames [(T_src - T) // 2, ... + T)) to T frames
+ * (:436-450), then per-sample flips along the frame axis / the width where flip_t[b] / flip_w[b] != 0 (RandFlipd spatial_axis
+ * 0 / 2 of create_3d_transforms :59-62; NULL = no flips).  Bit-identical to the CPU pipeline (true division). */
+int oct_ingest_u8(const uint8_t* src, float* dst, const uint8_t* flip_t, const uint8_t* flip_w, int64_t B, int64_t T_src,
+                  int64_t T, int64_t H, int64_t W, float divisor, oct_stream_t stream);
+
 /* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
 int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);
 

@@ -26,6 +26,7 @@ from typing import Dict, Optional
 
 import torch
 
+from . import ops
 from .dp import GradReducer
 from .models_mae import len_keep_of
 from .optim import FusedAdamW
@@ -104,35 +105,50 @@ class JointPretrainStep:
         return StepResult(out["loss"], out["loss_2d"] if joint else None, out["loss_all"], out["frame_loss"],
                           out["grad_norm"] if self.clip_grad is not None else None)
 
-    def __call__(self, samples, sample_2d=None, mask_ratio_2d: float = 0.75, noise=None, noise_2d=None) -> StepResult:
+    def __call__(self, samples, sample_2d=None, mask_ratio_2d: float = 0.75, noise=None, noise_2d=None, flips=None) -> StepResult:
         """samples [b,c,t,h,w] or [b,r,c,t,h,w] (engine_pretrain.py:101-103), sample_2d [b2,1,3,H,W] or None, both already on
-        the device.  `noise` / `noise_2d` (optional) replace the models' torch.rand draws for reproducible masks."""
-        if samples.dim() == 6:
+        the device.  `noise` / `noise_2d` (optional) replace the models' torch.rand draws for reproducible masks.
+        A uint8 `samples` [b, T_src, H, W] is the raw cube (1 byte per pixel over PCIe): ops.ingest_u8 scales, centre-pads /
+        crops it to the model's frame count and applies the per-sample `flips = (flip_t, flip_w)` ([b] uint8 flags or None)
+        while writing the step's fp32 input — on replayed steps straight into the graph's static buffer."""
+        cube = None
+        if samples.dtype == torch.uint8:
+            cube, frames = samples, self.model.patch_embed.frames
+            flip_t, flip_w = flips if flips is not None else (None, None)
+            samples = torch.empty(0)  # placeholder: only the shape below is used until the cube is ingested
+            vol_shape = (cube.shape[0], 1, frames, cube.shape[2], cube.shape[3])
+        elif samples.dim() == 6:
             b, r, c, t, h, w = samples.shape
             samples = samples.reshape(b * r, c, t, h, w)
+        if cube is None:
+            vol_shape = tuple(samples.shape)
         joint = sample_2d is not None
         if self._joint is not None and joint != self._joint:
             # another set of parameters takes part (quirk Q13): rebuild the buckets, forget graphs that point into the old ones
             self.reducer.reset()
             self._entries.clear()
         self._joint = joint
-        dev = samples.device
+        dev = cube.device if cube is not None else samples.device
         pe = self.model.high_res_patch_embed if joint else None
         keep_2d = len_keep_of(pe.input_size[1] * pe.input_size[2], mask_ratio_2d) if joint else None
-        key = (tuple(samples.shape), tuple(sample_2d.shape) if joint else None, keep_2d, noise is not None, noise_2d is not None)
+        key = (vol_shape, tuple(sample_2d.shape) if joint else None, keep_2d, noise is not None, noise_2d is not None)
         ent = self._entries.get(key)
         if ent is None:
-            tp = samples.shape[2] // self.model.patch_embed.t_patch_size
+            tp = vol_shape[2] // self.model.patch_embed.t_patch_size
             out = {"loss": torch.zeros((), device=dev), "loss_2d": torch.zeros((), device=dev),
-                   "loss_all": torch.zeros((), device=dev), "frame_loss": torch.zeros(samples.shape[0], tp, device=dev),
+                   "loss_all": torch.zeros((), device=dev), "frame_loss": torch.zeros(vol_shape[0], tp, device=dev),
                    "grad_norm": torch.zeros((), device=dev)}
             ent = self._entries[key] = {"calls": 0, "graph": None, "out": out}
         out = ent["out"]
         if not self.use_graph or ent["calls"] < self.warm_steps:
             ent["calls"] += 1
+            if cube is not None:
+                samples = ops.ingest_u8(cube, vol_shape[2], flip_t=flip_t, flip_w=flip_w)
             self._run(samples, sample_2d, mask_ratio_2d, noise, noise_2d, out)
             return self._result(out, joint)
         if ent["graph"] is None:
+            if cube is not None:
+                samples = ops.ingest_u8(cube, vol_shape[2], flip_t=flip_t, flip_w=flip_w)
             st = ent["static"] = {"vol": samples.clone(), "img": sample_2d.clone() if joint else None,
                                   "noise": noise.clone() if noise is not None else None,
                                   "noise_2d": noise_2d.clone() if noise_2d is not None else None}
@@ -144,7 +160,10 @@ class JointPretrainStep:
             ent["graph"] = graph
         else:
             st = ent["static"]
-            st["vol"].copy_(samples, non_blocking=True)
+            if cube is not None:
+                ops.ingest_u8(cube, vol_shape[2], out=st["vol"], flip_t=flip_t, flip_w=flip_w)
+            else:
+                st["vol"].copy_(samples, non_blocking=True)
             if joint:
                 st["img"].copy_(sample_2d, non_blocking=True)
             if noise is not None:

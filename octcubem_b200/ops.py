@@ -98,6 +98,22 @@ def patch_embed_tc(imgs, weight2d, bias, p, u, out_dtype=torch.bfloat16):
     return out
 
 
+def ingest_u8(cube_u8, T, out=None, flip_t=None, flip_w=None, divisor=255.0):
+    """uint8 cube [B, T_src, H, W] -> the step's fp32 input [B, 1, T, H, W]: /255, centre pad / crop to T frames, optional
+    per-sample flips ([B] uint8 flags) — the CPU work of PatientDataset_inhouse.py:420-450 + create_3d_transforms' RandFlipd,
+    bit-identical, written straight into `out` (e.g. the static input buffer of a captured step)."""
+    _chk(cube_u8, out, flip_t, flip_w)
+    assert cube_u8.dtype == torch.uint8 and cube_u8.dim() == 4
+    B, T_src, H, W = cube_u8.shape
+    if out is None:
+        out = torch.empty(B, 1, T, H, W, dtype=torch.float32, device=cube_u8.device)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (B, 1, T, H, W)
+    for f in (flip_t, flip_w):
+        assert f is None or (f.dtype == torch.uint8 and f.numel() == B)
+    _call("oct_ingest_u8", _p(cube_u8), _p(out), _p(flip_t), _p(flip_w), B, T_src, T, H, W, float(divisor), _stream())
+    return out
+
+
 def gemm(layout, A, B, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, aux=None, out=None, beta=0, compute=None):
     """D[M,N] = op(A) op(B) (+ epilogue); see include/octcube_b200.h for the layouts.  A, B 2-D contiguous."""
     _chk(A, B, bias, aux, out)

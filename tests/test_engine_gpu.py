@@ -73,6 +73,32 @@ def test_graph_replayed_steps_match_an_eager_torch_loop(joint):
         engine.close()
 
 
+def test_engine_uint8_cubes_equal_the_fp32_path():
+    """A uint8 cube through ops.ingest_u8 (eager steps: fresh tensor; replayed steps: straight into the graph's static input)
+    gives the same losses as feeding the CPU pipeline's fp32 volume."""
+    sd, _, _ = toy_inputs()
+    models = [build(sd, "fp32"), build(sd, "fp32")]
+    engines = []
+    for m in models:
+        opt = optim.FusedAdamW(optim.add_weight_decay(m, 0.05), betas=(0.9, 0.95),
+                               schedule=optim.CosineSchedule(1e-3, 1e-5, 1.0, 3.0, 0.5))
+        engines.append(JointPretrainStep(m, opt, mask_ratio=0.9, clip_grad=1.0, use_graph=True, warm_steps=2))
+    try:
+        for k in range(1, 5):
+            g = torch.Generator().manual_seed(50 + k)
+            cube = torch.randint(0, 256, (2, 10, 64, 64), generator=g, dtype=torch.uint8)      # 10 frames -> padded to 12
+            flip_t = torch.tensor([k % 2, 1], dtype=torch.uint8)
+            noise = O.synthetic_noise(2, 64, seed=60 + k).to(DEV)
+            vol = torch.cat([torch.zeros(2, 1, 64, 64), cube.float().div(255), torch.zeros(2, 1, 64, 64)], 1)
+            vol = torch.stack([v.flip(0) if f else v for v, f in zip(vol, flip_t)]).unsqueeze(1)
+            a = engines[0](cube.to(DEV), noise=noise, flips=(flip_t.to(DEV), None)).check_finite()
+            b = engines[1](vol.to(DEV), noise=noise).check_finite()
+            assert a["loss"] == pytest.approx(b["loss"], rel=1e-6) and a["grad_norm"] == pytest.approx(b["grad_norm"], rel=1e-5), k
+    finally:
+        for e in engines:
+            e.close()
+
+
 def test_engine_refuses_a_host_side_schedule_under_graphs():
     sd, _, _ = toy_inputs()
     m = build(sd, "fp32")

@@ -244,6 +244,39 @@ def test_colsum_unaligned_width(dtype):
     assert rel(got, x.float().sum(0)) < 1e-6
 
 
+# ---------------------------------------------------------------- volume ingest
+def _cpu_ingest(cube, T, flip_t, flip_w):
+    """The reference's CPU pipeline: ToTensor /255 (PatientDataset_inhouse.py:420), centre pad / crop of frames (:436-450),
+    RandFlipd along frames / width (create_3d_transforms :59-62)."""
+    out = []
+    for b in range(cube.shape[0]):
+        fr = cube[b].float().div(255)                      # [T_src, H, W]
+        n = fr.shape[0]
+        if n < T:
+            left = (T - n) // 2
+            fr = torch.cat([torch.zeros(left, *fr.shape[1:]), fr, torch.zeros(T - n - left, *fr.shape[1:])], 0)
+        elif n > T:
+            left = (n - T) // 2
+            fr = fr[left:-(n - T - left)]
+        if flip_t is not None and flip_t[b]:
+            fr = fr.flip(0)
+        if flip_w is not None and flip_w[b]:
+            fr = fr.flip(2)
+        out.append(fr)
+    return torch.stack(out).unsqueeze(1)
+
+
+@pytest.mark.parametrize("B,T_src,T,H,W", [(2, 12, 12, 64, 64), (3, 49, 60, 32, 256), (2, 61, 48, 16, 512), (1, 128, 60, 8, 36)])
+def test_ingest_u8_bit_exact(B, T_src, T, H, W):
+    g = torch.Generator().manual_seed(T_src)
+    cube = torch.randint(0, 256, (B, T_src, H, W), generator=g, dtype=torch.uint8)
+    flip_t = torch.randint(0, 2, (B,), generator=g, dtype=torch.uint8)
+    flip_w = 1 - flip_t if B > 1 else torch.ones(1, dtype=torch.uint8)
+    got = ops.ingest_u8(cube.to(DEV), T, flip_t=flip_t.to(DEV), flip_w=flip_w.to(DEV))
+    assert torch.equal(got.cpu(), _cpu_ingest(cube, T, flip_t, flip_w))
+    assert torch.equal(ops.ingest_u8(cube.to(DEV), T).cpu(), _cpu_ingest(cube, T, None, None))     # no flips
+
+
 # ---------------------------------------------------------------- loss
 @pytest.mark.parametrize("norm_pix", [False, True])
 @pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
