@@ -16,9 +16,12 @@ __global__ void __launch_bounds__(256) ingest_u8_kernel(const uint8_t* __restric
   const int b = blockIdx.y;
   const bool ft = flip_t && flip_t[b], fw = flip_w && flip_w[b];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * blockDim.x) {
-    const int w4 = (int)(i % W4);
-    const int h = (int)((i / W4) % H);
-    const int t = (int)(i / ((int64_t)W4 * H));
+    // 32-bit index arithmetic (the host checks T*H*W/4 < 2^31): three 64-bit divisions per item made the first version of
+    // this kernel instruction-bound (57 us for 25 M pixels, profiles/r1_membound_ncu.md)
+    const unsigned q = (unsigned)i / (unsigned)W4;
+    const int w4 = (int)((unsigned)i - q * (unsigned)W4);
+    const int t = (int)(q / (unsigned)H);
+    const int h = (int)(q - (unsigned)t * (unsigned)H);
     const int tp = ft ? T - 1 - t : t;     // frame of the padded / cropped cube that lands at output frame t
     const int ts = tp - shift;             // its index in the source cube (shift > 0: left padding, < 0: cropping)
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -41,7 +44,7 @@ extern "C" int oct_ingest_u8(const uint8_t* src, float* dst, const uint8_t* flip
   OCT_REQUIRE(B >= 0 && T_src > 0 && T > 0 && H > 0 && W > 0 && W % 4 == 0, "oct_ingest_u8: need positive sizes and W%%4==0");
   OCT_REQUIRE((reinterpret_cast<uintptr_t>(src) & 3) == 0 && aligned16(dst), "oct_ingest_u8: misaligned");
   OCT_REQUIRE(divisor > 0.f, "oct_ingest_u8: divisor must be positive");
-  OCT_REQUIRE(B <= 65535 && T * H * W < (1ll << 40), "oct_ingest_u8: too large");
+  OCT_REQUIRE(B <= 65535 && T * H * (W / 4) < (1ll << 31), "oct_ingest_u8: too large");
   if (B == 0) return OCT_OK;
   // PatientDataset_inhouse.py:439-450: left_padding = (T - T_src) // 2 zero frames, or frames [left_idx, left_idx + T)
   const int shift = T_src <= T ? (int)((T - T_src) / 2) : -(int)((T_src - T) / 2);
