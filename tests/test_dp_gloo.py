@@ -107,3 +107,46 @@ def test_reducer_single_process_is_identity():
     for (k, p), (_, r) in zip(net.named_parameters(), ref.named_parameters()):
         if r.grad is not None:
             assert torch.allclose(p.grad, r.grad, rtol=1e-6, atol=1e-7), k
+
+
+def _worker_accumulate(rank, world, port, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = Net()
+    red = GradReducer(net, bucket_mb=0.02, first_bucket_mb=0.005, last_bucket_mb=0.006)
+    x, y = torch.randn(4, 16), torch.randn(4, 8)
+    red.zero_grad()
+    ((net(x) - y) ** 2).mean().backward()
+    red.finish()                                   # discovery step
+    red.zero_grad()
+    ((net(x) - y) ** 2).mean().backward()
+    ((net(x) - y) ** 2).mean().backward()          # second pass into live gradients: buckets were already reduced
+    msg = ""
+    try:
+        red.finish()
+    except RuntimeError as e:
+        msg = str(e)
+    red.zero_grad()                                # the reducer stays usable afterwards
+    ((net(x) - y) ** 2).mean().backward()
+    red.finish()
+    if rank == 0:
+        torch.save(msg, path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_reducer_refuses_gradient_accumulation_across_ranks(tmp_path):
+    """Two backward passes before finish() at world size 2: the second pass's gradients were never reduced — finish() must
+    say so instead of handing back half-reduced gradients (dp.GradReducer.finish)."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    path = str(tmp_path / "msg.pt")
+    procs = [ctx.Process(target=_worker_accumulate, args=(r, 2, port, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(90)
+        assert p.exitcode == 0
+    assert "not reduced" in torch.load(path)
