@@ -2,6 +2,10 @@
 
 Drop-in for the reference's Pre-training/models_mae_joint_res_flash_attn.py:
     from octcubem_b200 import models_mae            # models_mae.__dict__[args.model](**vars(args))
+and, on the same kernels,
+    from octcubem_b200 import models_mae_flash_attn      # OCTCube/models_mae_flash_attn.py (2D MAE)
+    from octcubem_b200 import models_vit_st_flash_attn   # OCTCube/models_vit_st_flash_attn.py (encoder-only 3D ViT)
+    from octcubem_b200 import engine_pretrain, optim, dp # the loop body of engine_pretrain.py, AdamW + schedule, DDP's role
 The arithmetic lives in liboctcube_b200.so (hand-written CUDA, C ABI in include/octcube_b200.h).
 """
 from . import _lib  # noqa: F401
