@@ -60,6 +60,40 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -1 and "C%4" in _lib.last_error()
 
 
+def test_argument_validation_of_the_newer_entry_points(lib):
+    P = ctypes.c_void_p
+    # pooling: row range must lie inside the sequence, C % 4 == 0
+    assert lib.oct_mean_pool_ws_bytes(2, 1024, 1, 5121) == 2 * 80 * 1024 * 4          # 64-row chunks, fp32 partial sums
+    rc = lib.oct_mean_pool_fwd(P(16), 1, P(16), 0, 2, 10, 64, 3, 3, P(16), 1 << 20, None)
+    assert rc == -1 and "row0 < row1" in _lib.last_error()
+    rc = lib.oct_mean_pool_fwd(P(16), 1, P(16), 0, 2, 10, 64, 1, 10, P(16), 8, None)
+    assert rc == -3 and "workspace" in _lib.last_error()
+    rc = lib.oct_mean_pool_bwd(P(16), 0, P(16), 1, 2, 10, 66, 1, 10, None)
+    assert rc == -1 and "C%4" in _lib.last_error()
+    # ingest: W % 4, alignment, divisor
+    rc = lib.oct_ingest_u8(P(16), P(16), None, None, 2, 10, 12, 64, 62, 255.0, None)
+    assert rc == -1 and "W%4" in _lib.last_error()
+    rc = lib.oct_ingest_u8(P(18), P(16), None, None, 2, 10, 12, 64, 64, 255.0, None)
+    assert rc == -1 and "misaligned" in _lib.last_error()
+    rc = lib.oct_ingest_u8(P(16), P(16), None, None, 2, 10, 12, 64, 64, 0.0, None)
+    assert rc == -1 and "divisor" in _lib.last_error()
+    # optimizer clock: schedule sanity, alignment
+    rc = lib.oct_adamw_clock_advance(P(16), 1e-3, 1e-5, 5.0, 5.0, 0.01, 0.9, 0.95, None)
+    assert rc == -1 and "schedule" in _lib.last_error()
+    rc = lib.oct_adamw_clock_advance(P(8), 1e-3, 1e-5, 1.0, 5.0, 0.01, 0.9, 0.95, None)
+    assert rc == -1 and "aligned" in _lib.last_error()
+    rc = lib.oct_adamw_step_clocked(P(16), 4, None, 1.0, 0.9, 0.95, 1e-8, 0.05, 1.0, None, None)
+    assert rc == -1 and "clock" in _lib.last_error()
+    # un-shuffle: a per-sample cls row (y_row0 = 1) needs the cls row to exist
+    rc = lib.oct_unshuffle_fwd(P(16), 1, P(16), P(16), P(16), None, None, P(16), 2, 16, 4, 16, 32, 1, None)
+    assert rc == -1 and "y_row0" in _lib.last_error()
+    rc = lib.oct_unshuffle_fwd(P(16), 1, P(16), P(16), P(16), None, P(16), P(16), 2, 16, 4, 16, 32, 2, None)
+    assert rc == -1 and "y_row0" in _lib.last_error()
+    # loss: the 2D model's channel-last order needs T == u and no frame index
+    rc = lib.oct_mse_loss_fwd(P(16), None, P(16), 0, P(16), P(16), P(16), P(16), P(16), 2, 12, 12, 64, 64, 16, 3, 65, 1, 2, None)
+    assert rc == -1 and "channel-last" in _lib.last_error()
+
+
 def test_no_cpu_fallback():
     """Product ops refuse CPU tensors instead of silently computing with torch."""
     import torch
