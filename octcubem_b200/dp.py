@@ -19,6 +19,7 @@ Works on CPU tensors with the gloo backend (used by the world_size-2 tests) — 
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional
 
 import torch
@@ -36,6 +37,7 @@ class _Bucket:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         self.pending = len(params)
+        self.launched = False
         self.work = None
 
 
@@ -57,6 +59,7 @@ class GradReducer:
         self._discovering = True
         self._prescaled = False
         self._stream_used = False
+        self._no_sync = False
         dev = next(model.parameters()).device
         self.device = dev
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
@@ -128,12 +131,15 @@ class GradReducer:
             if p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
                 p.grad = view
+            if self._no_sync:  # a micro-step of an accumulation group: keep the sum local
+                return
             b.pending -= 1
             if b.pending == 0:
                 self._launch(b)
         return hook
 
     def _launch(self, b: _Bucket):
+        b.launched = True
         if self.world == 1:
             return
         if self.stream is not None:
@@ -150,6 +156,20 @@ class GradReducer:
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     # ------------------------------------------------------------------ step protocol
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Micro-steps 1 .. k-1 of a gradient-accumulation group (the role of DistributedDataParallel.no_sync): gradients
+        accumulate in the buckets, nothing is reduced, finish() is not called.  The LAST micro-step runs outside this context
+        and reduces the accumulated sums.  Use the same backward style (reducer.backward or loss.backward) for all of them;
+        the bucket-discovery step cannot be a micro-step."""
+        if self._discovering:
+            raise RuntimeError("GradReducer.no_sync(): run one ordinary step first (bucket discovery)")
+        self._no_sync = True
+        try:
+            yield
+        finally:
+            self._no_sync = False
+
     def backward(self, loss: torch.Tensor):
         """loss.backward() with the gradient seeded at 1 / world: the summed gradients are DDP's averages as they leave the
         collective.  Follow with finish() as usual."""
@@ -179,16 +199,32 @@ class GradReducer:
                     if not self._prescaled:
                         b.flat.mul_(1.0 / self.world)
                     b.work = None
-        if self.world > 1 and not discovery and any(b.pending != 0 for b in self.buckets):
-            # a gradient that never reached its hook: e.g. a second backward() into gradients that were not cleared — the
-            # in-place weight-gradient sinks then accumulate without telling autograd, and this bucket was never reduced
-            stuck = [n for b in self.buckets if b.pending != 0 for n in b.names][:4]
-            for b in self.buckets:
-                b.pending = len(b.params)
-            raise RuntimeError("GradReducer.finish(): some buckets were not reduced on this step (gradient accumulation over "
-                               f"several backward passes is only supported at world size 1); first parameters: {stuck}")
+        if not discovery:
+            if self.world > 1 and any(b.pending < 0 for b in self.buckets):
+                # gradients kept arriving after a bucket had been reduced: a second backward() into live gradients without
+                # no_sync() around the first — the sums in the buckets are part reduced, part local
+                stuck = [n for b in self.buckets if b.pending < 0 for n in b.names][:4]
+                for b in self.buckets:
+                    b.pending, b.launched = len(b.params), False
+                raise RuntimeError("GradReducer.finish(): some buckets were reduced before all of their gradients had arrived "
+                                   "(wrap all but the last backward pass of an accumulation group in reducer.no_sync()); "
+                                   f"first parameters: {stuck}")
+            late = [b for b in self.buckets if not b.launched]
+            # buckets whose hooks did not all fire: after no_sync() micro-steps the in-place weight-gradient sinks accumulate
+            # without going through autograd (ops._sink), so the last pass cannot count them — reduce those buckets now
+            for b in late:
+                self._launch(b)
+            if late and self.stream is not None and self._stream_used:
+                torch.cuda.current_stream(self.device).wait_stream(self.stream)
+                self._stream_used = False
+            for b in late:
+                if b.work is not None:
+                    b.work.wait()
+                    if not self._prescaled:
+                        b.flat.mul_(1.0 / self.world)
+                    b.work = None
         for b in self.buckets:
-            b.pending = len(b.params)
+            b.pending, b.launched = len(b.params), False
         self._prescaled = False
 
     def zero_grad(self):

@@ -138,8 +138,8 @@ def _worker_accumulate(rank, world, port, path):
 
 @pytest.mark.timeout(120)
 def test_reducer_refuses_gradient_accumulation_across_ranks(tmp_path):
-    """Two backward passes before finish() at world size 2: the second pass's gradients were never reduced — finish() must
-    say so instead of handing back half-reduced gradients (dp.GradReducer.finish)."""
+    """Two backward passes before finish() at world size 2 without no_sync(): the buckets were reduced after the first pass and
+    the second pass added local gradients on top — finish() must say so instead of handing back half-reduced gradients."""
     port = _free_port()
     ctx = mp.get_context("spawn")
     path = str(tmp_path / "msg.pt")
@@ -149,4 +149,121 @@ def test_reducer_refuses_gradient_accumulation_across_ranks(tmp_path):
     for p in procs:
         p.join(90)
         assert p.exitcode == 0
-    assert "not reduced" in torch.load(path)
+    assert "no_sync" in torch.load(path)
+
+
+def _worker_no_sync(rank, world, port, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = Net()
+    red = GradReducer(net, bucket_mb=0.02, first_bucket_mb=0.005, last_bucket_mb=0.006)
+    g = torch.Generator().manual_seed(3)
+    X, Y = torch.randn(16, 16, generator=g), torch.randn(16, 8, generator=g)
+    red.zero_grad()
+    ((net(X[:2]) - Y[:2]) ** 2).mean().backward()
+    red.finish()                                              # discovery step (its result is not used)
+    out = {}
+    for style in ("seeded", "plain"):
+        red.zero_grad()
+        micro = X.chunk(2), Y.chunk(2)                        # accumulation group of 2 micro-steps of global batch 8
+        for k in range(2):
+            x, y = micro[0][k].chunk(world)[rank], micro[1][k].chunk(world)[rank]
+            loss = ((net(x) - y) ** 2).mean() / 2             # loss /= accum_iter (engine_pretrain.py:163)
+            if k == 0:
+                with red.no_sync():
+                    red.backward(loss) if style == "seeded" else loss.backward()
+            else:
+                red.backward(loss) if style == "seeded" else loss.backward()
+                red.finish()
+        out[style] = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    if rank == 0:
+        torch.save(out, path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_reducer_no_sync_accumulates_then_reduces(tmp_path):
+    """reducer.no_sync() (DDP.no_sync's role): two micro-steps on two ranks == one pass over the 16 samples with the mean loss."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    path = str(tmp_path / "acc.pt")
+    procs = [ctx.Process(target=_worker_no_sync, args=(r, 2, port, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(90)
+        assert p.exitcode == 0
+    got = torch.load(path)
+    torch.manual_seed(0)
+    net = Net()
+    g = torch.Generator().manual_seed(3)
+    X, Y = torch.randn(16, 16, generator=g), torch.randn(16, 8, generator=g)
+    ((net(X) - Y) ** 2).mean().backward()
+    for style in ("seeded", "plain"):
+        assert set(got[style]) == {n for n, p in net.named_parameters() if p.grad is not None}
+        for n, p in net.named_parameters():
+            if p.grad is not None:
+                assert torch.allclose(got[style][n], p.grad, rtol=1e-5, atol=1e-7), (style, n)
+
+
+class BranchNet(Net):
+    """`unused` takes part only when asked to: on the last micro-step its hooks do not fire, like the in-place weight-gradient
+    sinks of the CUDA path (ops._sink) that accumulate without going through autograd."""
+
+    def forward(self, x, extra=False):
+        h = torch.tanh(self.front(x))
+        if extra:
+            h = h + torch.tanh(self.unused(x))
+        for b in self.blocks:
+            h = h + torch.tanh(b(h))
+        return self.head(h)
+
+
+def _worker_late_bucket(rank, world, port, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = BranchNet()
+    red = GradReducer(net, bucket_mb=0.02, first_bucket_mb=0.005, last_bucket_mb=0.006)
+    g = torch.Generator().manual_seed(4)
+    X, Y = torch.randn(16, 16, generator=g), torch.randn(16, 8, generator=g)
+    red.zero_grad()
+    ((net(X[:2], extra=True) - Y[:2]) ** 2).mean().backward()
+    red.finish()                                              # discovery with every parameter taking part
+    red.zero_grad()
+    for k in range(2):
+        x, y = X.chunk(2)[k].chunk(world)[rank], Y.chunk(2)[k].chunk(world)[rank]
+        loss = ((net(x, extra=(k == 0)) - y) ** 2).mean() / 2
+        if k == 0:
+            with red.no_sync():
+                red.backward(loss)
+        else:
+            red.backward(loss)                                # `unused.*` gets no gradient in this pass: its bucket is late
+            red.finish()
+    if rank == 0:
+        torch.save({n: p.grad.clone() for n, p in net.named_parameters()}, path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_reducer_reduces_buckets_whose_hooks_did_not_fire_on_the_last_micro_step(tmp_path):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    path = str(tmp_path / "late.pt")
+    procs = [ctx.Process(target=_worker_late_bucket, args=(r, 2, port, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(90)
+        assert p.exitcode == 0
+    got = torch.load(path)
+    torch.manual_seed(0)
+    net = BranchNet()
+    g = torch.Generator().manual_seed(4)
+    X, Y = torch.randn(16, 16, generator=g), torch.randn(16, 8, generator=g)
+    (((net(X[:8], extra=True) - Y[:8]) ** 2).mean() / 2 + ((net(X[8:]) - Y[8:]) ** 2).mean() / 2).backward()
+    for n, p in net.named_parameters():
+        assert torch.allclose(got[n], p.grad, rtol=1e-5, atol=1e-7), n
