@@ -141,7 +141,7 @@ def main_reference(args):
 
 def workload_name():
     return (f"3D MAE ViT-L/16 t_patch 3 + dec 512x8x16, {FRAMES}x{IMG}x{IMG} volumes, mask {MASK}, bf16 fwd+bwd, "
-            f"batch {BATCH}/GPU (BASELINE.json configs[1])")
+            f"batch {BATCH}/GPU (BASELINE.json configs[{1 if FRAMES == 48 else 2}])")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -460,7 +460,10 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=FRAMES, choices=sorted(GF_PER_VOLUME),
+                    help="48 = BASELINE.json configs[1] (the default and the driver's workload); 60 = the cfg-3 volume size")
     a = ap.parse_args()
+    FRAMES = a.frames
     if a.impl == "reference":
         main_reference(a)
     else:
