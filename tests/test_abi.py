@@ -94,6 +94,22 @@ def test_argument_validation_of_the_newer_entry_points(lib):
     assert rc == -1 and "channel-last" in _lib.last_error()
 
 
+def test_compute_entry_points_fail_loudly_without_a_device(lib):
+    """No GPU (this container): a compute call returns an error code and a message — it neither crashes nor computes."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    P = ctypes.c_void_p
+    rc = lib.oct_gemm(1, 0, P(1 << 20), P(2 << 20), P(3 << 20), 1, 256, 256, 256, 256, 256, 256, 0, None, None, 0, None)
+    assert rc != 0 and _lib.last_error()
+    rc = lib.oct_attn_fwd(1, P(1 << 20), P(2 << 20), P(3 << 20), 2, 64, 2, 32, 0.17, None)
+    assert rc != 0 and _lib.last_error()
+    rc = lib.oct_add_ln_fwd(P(1 << 20), 1, None, None, P(2 << 20), P(3 << 20), P(4 << 20), 1, P(5 << 20), P(6 << 20), 16, 64, 1e-6, None)
+    assert rc != 0 and "oct_add_ln_fwd" in _lib.last_error()
+    rc = lib.oct_ingest_u8(P(1 << 20), P(2 << 20), None, None, 2, 10, 12, 64, 64, 255.0, None)
+    assert rc != 0 and "oct_ingest_u8" in _lib.last_error()
+
+
 def test_no_cpu_fallback():
     """Product ops refuse CPU tensors instead of silently computing with torch."""
     import torch
