@@ -139,9 +139,10 @@ def main_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_name():
-    return (f"3D MAE ViT-L/16 t_patch 3 + dec 512x8x16, {FRAMES}x{IMG}x{IMG} volumes, mask {MASK}, bf16 fwd+bwd, "
-            f"batch {BATCH}/GPU (BASELINE.json configs[{1 if FRAMES == 48 else 2}])")
+def workload_name(frames=None):
+    frames = FRAMES if frames is None else frames
+    return (f"3D MAE ViT-L/16 t_patch 3 + dec 512x8x16, {frames}x{IMG}x{IMG} volumes, mask {MASK}, bf16 fwd+bwd, "
+            f"batch {BATCH}/GPU (BASELINE.json configs[{1 if frames == 48 else 2}])")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -153,10 +154,96 @@ def _watchdog(seconds):
     os._exit(3)
 
 
+class StepBench:
+    """One configuration (frame count) of the step on this rank: model, optional reducer, eager warm-up, CUDA graph."""
+
+    def __init__(self, frames, args, dev, world, rank, lib, use_reducer=True):
+        import torch.distributed as dist
+        from octcubem_b200 import models_mae
+        from octcubem_b200.dp import GradReducer
+        self.frames, self.dev, self.world = frames, dev, world
+        torch.manual_seed(1234)
+        model = models_mae.flash_attn_mae_vit_large_patch16(
+            input_size=IMG, in_chans=1, num_frames=frames, t_patch_size=3, pred_t_dim=frames, sep_pos_embed=True,
+            cls_embed=True, high_res_input_size=512, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16,
+            precision="bf16").to(dev)
+        if world > 1:  # same weights on every rank (DDP broadcasts rank 0's at construction)
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        bucket_mb = float(os.environ.get("OCT_BUCKET_MB", "32"))  # experiment knob; 32 MB is the measured default
+        self.model = model
+        self.reducer = GradReducer(model, bucket_mb=bucket_mb) if (world > 1 and use_reducer) else None
+        g = torch.Generator().manual_seed(100 + rank)
+        host_vol = torch.rand(BATCH, 1, frames, IMG, IMG, generator=g)
+        host_vol[:, :, :3] = 0; host_vol[:, :, -3:] = 0       # centre-padding of PatientDataset_inhouse.py:439-444
+        self.host_vol = host_vol.pin_memory()
+        self.vol = self.host_vol.to(dev)
+        self.loss_out = torch.zeros((), device=dev)
+        # eager warm-up (also: TMA maps / func attributes / reducer bucket discovery), launch count of one step
+        for _ in range(2):
+            self.step()
+        torch.cuda.synchronize()
+        c0 = lib.oct_launch_count()
+        self.step()
+        torch.cuda.synchronize()
+        self.launches_per_step = int(lib.oct_launch_count() - c0)
+        self.graph = None
+        if not args.no_graph:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self.step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.step()
+                self.graph.replay()
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa
+                if rank == 0:
+                    print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                self.graph = None
+                torch.cuda.synchronize()
+
+    def step(self):
+        model, reducer = self.model, self.reducer
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            model.zero_grad(set_to_none=True)
+        loss, _, _ = model(self.vol, mask_ratio=MASK)           # noise drawn on device, like models...:350
+        if reducer is not None:
+            reducer.backward(loss)                              # seeded with 1/world: the all-reduce yields DDP's mean
+            reducer.finish()
+        else:
+            loss.backward()
+        self.loss_out.copy_(loss.detach())
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.step()
+
+    def close(self):
+        """Drop the captured graph (it holds NCCL kernels of the process group) and the reducer's hooks / buckets."""
+        self.graph = None
+        if self.reducer is not None:
+            self.reducer.remove()
+            self.reducer = None
+        self.model = None
+        self.vol = self.host_vol = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+
 def main_b200(args):
     import torch.distributed as dist
-    from octcubem_b200 import _lib, models_mae, ops
-    from octcubem_b200.dp import GradReducer
+    from octcubem_b200 import _lib, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -170,69 +257,6 @@ def main_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     pk = peaks()
-
-    torch.manual_seed(1234)
-    model = models_mae.flash_attn_mae_vit_large_patch16(
-        input_size=IMG, in_chans=1, num_frames=FRAMES, t_patch_size=3, pred_t_dim=FRAMES, sep_pos_embed=True,
-        cls_embed=True, high_res_input_size=512, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16,
-        precision="bf16").to(dev)
-    if world > 1:  # same weights on every rank (DDP broadcasts rank 0's at construction)
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-    bucket_mb = float(os.environ.get("OCT_BUCKET_MB", "32"))  # experiment knob; 32 MB is the measured default
-    reducer = GradReducer(model, bucket_mb=bucket_mb) if world > 1 else None
-    L = (FRAMES // 3) * (IMG // 16) ** 2
-
-    g = torch.Generator().manual_seed(100 + rank)
-    host_vol = torch.rand(BATCH, 1, FRAMES, IMG, IMG, generator=g)
-    host_vol[:, :, :3] = 0; host_vol[:, :, -3:] = 0           # centre-padding of PatientDataset_inhouse.py:439-444
-    host_vol = host_vol.pin_memory()
-    vol = host_vol.to(dev)
-    loss_out = torch.zeros((), device=dev)
-
-    def step(v):
-        if reducer is not None:
-            reducer.zero_grad()
-        else:
-            model.zero_grad(set_to_none=True)
-        loss, _, _ = model(v, mask_ratio=MASK)                  # noise drawn on device, like models...:350
-        if reducer is not None:
-            reducer.backward(loss)                              # seeded with 1/world: the all-reduce yields DDP's mean
-            reducer.finish()
-        else:
-            loss.backward()
-        loss_out.copy_(loss.detach())
-
-    # eager warm-up (also: TMA maps / func attributes / reducer bucket discovery), launch count of one step
-    for _ in range(2):
-        step(vol)
-    torch.cuda.synchronize()
-    c0 = lib.oct_launch_count()
-    step(vol)
-    torch.cuda.synchronize()
-    launches_per_step = int(lib.oct_launch_count() - c0)
-
-    graph = None
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step(vol)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step(vol)
-            graph.replay()
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa
-            if rank == 0:
-                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
-
-    run = (lambda: graph.replay()) if graph is not None else (lambda: step(vol))
 
     def barrier():
         if world > 1:
@@ -253,6 +277,10 @@ def main_b200(args):
         barrier()
         return float(ms)
 
+    sb = StepBench(FRAMES, args, dev, world, rank, lib)
+    model, vol, host_vol, loss_out = sb.model, sb.vol, sb.host_vol, sb.loss_out
+    launches_per_step, run = sb.launches_per_step, sb.run
+    graph_used = sb.graph is not None
     for _ in range(max(args.warmup, 3)):
         run()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -293,37 +321,98 @@ def main_b200(args):
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * BATCH / (e2e_ms / 1e3)
     last_loss = float(loss_out)
+    torch.cuda.synchronize()
+    del stage
+
+    # N > 1: the same step WITHOUT the gradient exchange (local gradients only) on the same build, same box: the difference
+    # to the step above is the communication that backward does not hide (plus NCCL's SM footprint while it overlaps)
+    comm = None
+    if world > 1 and not args.no_extras:
+        try:
+            used_graph = sb.graph is not None
+            sb.graph = None
+            sb.reducer.remove()
+            sb.reducer = None
+            torch.cuda.synchronize()
+            for _ in range(2):
+                sb.step()
+            torch.cuda.synchronize()
+            g2 = None
+            if used_graph:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    sb.step()
+            local_run = g2.replay if g2 is not None else sb.step
+            for _ in range(3):
+                local_run()
+            ms_local = timed(local_run, args.steps) / args.steps
+            comm = {"step_ms_without_exchange": ms_local, "exposed_comm_ms": ms_step - ms_local,
+                    "note": "same ranks, same build; the reducer removed, gradients stay local"}
+            del g2
+        except Exception as e:  # noqa
+            if rank == 0:
+                print(f"[bench] no-exchange timing skipped ({type(e).__name__}: {e})", file=sys.stderr)
 
     # roofline of the dominant kernel, timed alone at its in-step shape (CUDA events on the launching stream)
     roof = dominant_kernel_roofline(ops, dev, pk)
 
-
     # optimizer step, informational (not on the hot path): our fused multi-tensor AdamW (one launch per
     # parameter group, also emits the bf16 weight shadows) next to torch's fused AdamW on the same parameters
     opt_ms = opt_torch_ms = None
-    try:
-        from octcubem_b200 import optim
-        opt = optim.FusedAdamW(optim.add_weight_decay(model, 0.05), lr=1e-6, betas=(0.9, 0.95), shadows=model.shadow_of)
-        for _ in range(2):
-            opt.step()
-        opt_ms = timed(opt.step, 5) / 5
-        model.shadows_current()
-        topt = torch.optim.AdamW(optim.add_weight_decay(model, 0.05), lr=1e-6, betas=(0.9, 0.95), fused=True)
-        for _ in range(2):
-            topt.step()
-        opt_torch_ms = timed(topt.step, 5) / 5
-    except Exception as e:  # noqa
-        if rank == 0:
-            print(f"[bench] optimizer timing skipped ({type(e).__name__}: {e})", file=sys.stderr)
+    if not args.no_extras:
+        try:
+            from octcubem_b200 import optim
+            if sb.reducer is None and world > 1:
+                sb.step()                                           # plain gradients again after the reducer was removed
+            opt = optim.FusedAdamW(optim.add_weight_decay(model, 0.05), lr=1e-6, betas=(0.9, 0.95), shadows=model.shadow_of)
+            for _ in range(2):
+                opt.step()
+            opt_ms = timed(opt.step, 5) / 5
+            model.shadows_current()
+            topt = torch.optim.AdamW(optim.add_weight_decay(model, 0.05), lr=1e-6, betas=(0.9, 0.95), fused=True)
+            for _ in range(2):
+                topt.step()
+            opt_torch_ms = timed(topt.step, 5) / 5
+            del opt, topt
+        except Exception as e:  # noqa
+            if rank == 0:
+                print(f"[bench] optimizer timing skipped ({type(e).__name__}: {e})", file=sys.stderr)
 
     # the north star's encoder target: forward + backward of forward_encoder alone (patch-embed, masking, 24 ViT-L blocks
     # at S = 410, final norm), as one CUDA graph, against the tensor-pipe peak
     enc = None                                                   # (after the optimizer timing: it drops the step's gradients)
-    if world == 1:
+    if world == 1 and not args.no_extras:
         try:
             enc = encoder_step(model, vol, pk, timed, args.steps)
         except Exception as e:  # noqa
             print(f"[bench] encoder-step timing skipped ({type(e).__name__}: {e})", file=sys.stderr)
+    model = vol = host_vol = None
+    sb.close()
+
+    # BASELINE configs[2] (cfg-3): the same step on 60x256x256 volumes (S_dec = 5121, keep = 511), same N, same build
+    cfg3 = None
+    other = 60 if FRAMES == 48 else 48
+    if not args.no_extras:
+        try:
+            sb3 = StepBench(other, args, dev, world, rank, lib)
+            for _ in range(3):
+                sb3.run()
+            ms3 = timed(sb3.run, args.steps) / args.steps
+            cfg3 = {"workload": workload_name(other), "value": world * BATCH / (ms3 / 1e3), "unit": "volumes/s",
+                    "ms_per_step": ms3, "steps": args.steps, "cuda_graph": sb3.graph is not None,
+                    "step_tflops_per_gpu": GF_PER_VOLUME[other] * BATCH / ms3,
+                    "step_frac_of_bf16_sustained": GF_PER_VOLUME[other] * BATCH / ms3 / pk["bf16_sustained"]}
+            sb3.close()
+            del sb3
+        except Exception as e:  # noqa
+            if rank == 0:
+                print(f"[bench] {other}-frame configuration skipped ({type(e).__name__}: {e})", file=sys.stderr)
+
+    # the GPU incumbent on the same box: the reference's own flash model (flash_attn Blocks + nn.Conv3d under bf16 autocast,
+    # oracle/gpu_incumbent.py — test infrastructure, never on the product path), same config, same precision
+    incumbent = None
+    if world == 1 and not args.no_extras and not args.no_incumbent:
+        incumbent = incumbent_block(dev, timed, args.steps)
 
     if rank == 0:
         gf = GF_PER_VOLUME[FRAMES]
@@ -331,12 +420,12 @@ def main_b200(args):
             "metric": "3D-MAE pretrain volumes/sec", "value": value, "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(), "global_batch": world * BATCH, "parallelism": f"dp{world}",
+            "config": {"workload": workload_name(FRAMES), "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "step": "forward + backward" + (" + NCCL gradient all-reduce overlapped with backward" if world > 1 else "")
                                + "; optimizer excluded (SURVEY §8d), see optimizer_ms",
-                       "cuda_graph": graph is not None,
+                       "cuda_graph": bool(graph_used),
                        "l2": "per-step working set (1.3 GB fp32 weights + bf16 shadows + ~10 GB activations) >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": "volumes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": host_vol.numel() * 4 * 1,
+            "e2e": {"value": e2e_value, "unit": "volumes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": BATCH * FRAMES * IMG * IMG * 4,
                     "d2h_bytes_per_step": 4,
                     "pipeline": "upload of step i+1 (pinned, copy stream, staging buffer) overlaps step i; one H2D per timed step"},
             "gpu_launches": launches_per_step * args.steps,
@@ -346,6 +435,9 @@ def main_b200(args):
             "step_frac_of_bf16_sustained": gf * BATCH / ms_step / pk["bf16_sustained"],
             "roofline": roof,
             "encoder_step": enc,
+            "cfg3" if other == 60 else "cfg2": cfg3,
+            "comm": comm,
+            "incumbent": incumbent,
             "optimizer_ms": opt_ms,
             "optimizer_torch_fused_ms": opt_torch_ms,
             "loss": last_loss,
@@ -356,12 +448,31 @@ def main_b200(args):
             line["cpu_baseline"] = {"value": r["value"], "unit": "volumes/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
-    # leave without NCCL teardown: destroying a communicator whose kernels live in a captured graph can block; every
-    # rank has passed the final barrier inside timed(), nothing else is in flight
     sys.stdout.flush()
     sys.stderr.flush()
+    # orderly exit (interpreter exit hooks run): every graph that held NCCL kernels has been destroyed above, so the
+    # communicator can be torn down; a hung teardown is cut short by the exit watchdog rather than by skipping the hooks
     torch.cuda.synchronize()
+    if world > 1:
+        barrier()
+        threading.Thread(target=_exit_watchdog, args=(60,), daemon=True).start()
+        dist.destroy_process_group()
+
+
+def _exit_watchdog(seconds):
+    time.sleep(seconds)
+    print(f"[bench] process-group teardown still running after {seconds} s; leaving", file=sys.stderr, flush=True)
     os._exit(0)
+
+
+def incumbent_block(dev, timed, steps):
+    """Same-box numbers of the stack the reference runs on a GPU (SURVEY §2.2 'bar'): its flash model under bf16 autocast,
+    eager like the reference's loop and as a CUDA graph, plus flash_attn's kernels alone at the two attention shapes."""
+    try:
+        from oracle import gpu_incumbent as G
+        return G.bench_block(FRAMES, IMG, BATCH, MASK, dev, timed, min(steps, 10))
+    except Exception as e:  # noqa
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
 # algorithmic GF per volume of the encoder blocks, forward (SURVEY §8d: 24 x (24 S dim^2 + 4 S^2 dim), S = keep + 1)
@@ -460,6 +571,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e + roofline only (no encoder / cfg-3 / optimizer / incumbent legs)")
+    ap.add_argument("--no-incumbent", action="store_true")
     ap.add_argument("--frames", type=int, default=FRAMES, choices=sorted(GF_PER_VOLUME),
                     help="48 = BASELINE.json configs[1] (the default and the driver's workload); 60 = the cfg-3 volume size")
     a = ap.parse_args()

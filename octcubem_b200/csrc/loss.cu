@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
     const int r = blockIdx.x;  // dpred row
     j = r - pred_row0;
     TD* drow = dpred + ((size_t)b * pred_rows + r) * P;
-    const bool live = (j >= 0) && (mask[(size_t)b * L + j] != 0.f);
+    const bool live = (j >= 0) && (j < L) && (mask[(size_t)b * L + j] != 0.f);  // rows past the L tokens: zero gradient
     if (!live) {
       for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) Vec4<TD>::st(drow + e4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
       return;
@@ -112,28 +112,38 @@ __global__ void __launch_bounds__(1024) mse_loss_finish_kernel(const float* loss
                                                                     float* loss, float* mask_sum, float* frame_losses,
                                                                     int BT, int G) {
   __shared__ float part[2 * 4096];
+  __shared__ float tot[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int g = warp; g < BT; g += nw) {
-    float ls = 0.f, ms = 0.f;
-    for (int s = lane; s < G; s += 32) {
-      const float m = mask[(size_t)g * G + s];
-      ls += loss_tok[(size_t)g * G + s] * m;
-      ms += m;
+  if (threadIdx.x == 0) { tot[0] = 0.f; tot[1] = 0.f; }
+  for (int base = 0; base < BT; base += 4096) {  // any B * T': 4096 (b,t') groups per pass, totals carried in a fixed order
+    const int n = min(4096, BT - base);
+    for (int i = warp; i < n; i += nw) {
+      const int g = base + i;
+      float ls = 0.f, ms = 0.f;
+      for (int s = lane; s < G; s += 32) {
+        const float m = mask[(size_t)g * G + s];
+        ls += loss_tok[(size_t)g * G + s] * m;
+        ms += m;
+      }
+      ls = warp_sum(ls);
+      ms = warp_sum(ms);
+      if (lane == 0) {
+        part[i] = ls;
+        part[4096 + i] = ms;
+        frame_losses[g] = ls / (ms + 1e-6f);
+      }
     }
-    ls = warp_sum(ls);
-    ms = warp_sum(ms);
-    if (lane == 0) {
-      part[g] = ls;
-      part[4096 + g] = ms;
-      frame_losses[g] = ls / (ms + 1e-6f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float ls = tot[0], ms = tot[1];
+      for (int i = 0; i < n; ++i) { ls += part[i]; ms += part[4096 + i]; }
+      tot[0] = ls; tot[1] = ms;
     }
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
-    float ls = 0.f, ms = 0.f;
-    for (int g = 0; g < BT; ++g) { ls += part[g]; ms += part[4096 + g]; }
-    loss[0] = ls / ms;
-    mask_sum[0] = ms;
+    loss[0] = tot[0] / tot[1];
+    mask_sum[0] = tot[1];
   }
 }
 

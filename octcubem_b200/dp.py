@@ -27,15 +27,19 @@ import torch.distributed as dist
 
 
 class _Bucket:
+    ALIGN = 32  # elements (fp32): 128 bytes
+
     def __init__(self, params: List[torch.nn.Parameter], names: List[str], device, dtype):
         self.params, self.names = params, names
-        self.numel = sum(p.numel() for p in params)
-        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)
-        self.views = []
-        off = 0
+        # every view starts on a 128-byte boundary: the optimizer / grad-norm kernels use float4 accesses on `param.grad` and
+        # the wgrad kernels reach the views through TMA (16-byte alignment), whatever the numel of the tensors in front
+        offs, off = [], 0
         for p in params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            offs.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.numel = off
+        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)   # (padding stays zero: a SUM all-reduce keeps it zero)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
         self.pending = len(params)
         self.launched = False
         self.work = None
@@ -114,7 +118,8 @@ class GradReducer:
         self._sink_keys = []
 
     def bucket_layout(self):
-        return [(b.names, b.numel) for b in (self.buckets or [])]
+        """[(parameter names, payload elements)] per bucket (the flat buffers are a little longer: 128-byte aligned views)."""
+        return [(b.names, sum(p.numel() for p in b.params)) for b in (self.buckets or [])]
 
     # ------------------------------------------------------------------ hooks
     def _make_hook(self, name):

@@ -22,6 +22,7 @@ own graph.  bf16 needs no loss scaling, so NativeScaler's GradScaler is not repr
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import torch
@@ -69,7 +70,7 @@ class StepResult:
 
 class JointPretrainStep:
     def __init__(self, model, optimizer: FusedAdamW, mask_ratio: float = 0.9, clip_grad: Optional[float] = None,
-                 accum_iter: int = 1, use_graph: bool = True, warm_steps: int = 2, process_group=None):
+                 accum_iter: int = 1, use_graph: bool = True, warm_steps: int = 2, process_group=None, max_graphs: int = 2):
         if accum_iter != 1:
             raise NotImplementedError("JointPretrainStep: accum_iter > 1 is not implemented (the reference recipe uses 1 per GPU batch)")
         if use_graph and optimizer.schedule is None:
@@ -79,8 +80,16 @@ class JointPretrainStep:
         self.mask_ratio, self.clip_grad = mask_ratio, clip_grad
         self.use_graph, self.warm_steps = use_graph, max(2, int(warm_steps))  # bucket discovery + one bucketed step
         self.reducer = GradReducer(model, process_group)
-        self._entries: Dict[tuple, dict] = {}
+        # graphs per input signature, least recently used first.  `mask_ratio_2d_scheduler` walks through ~100 keep counts
+        # over a run (one per epoch): only the newest `max_graphs` signatures keep their graph, and all graphs allocate
+        # from ONE private pool (they replay strictly one after another), so memory does not grow with the epoch count
+        self.max_graphs = max(1, int(max_graphs))
+        self._entries: "OrderedDict[tuple, dict]" = OrderedDict()
+        self._pool = None
         self._joint: Optional[bool] = None
+        # the bf16 path's GEMMs read bf16 weight shadows: either the optimizer writes them (shadows=model.shadow_of) and the
+        # model is told so after every step, or nobody marks them current and the forward re-casts from the fp32 masters
+        self._opt_writes_shadows = bool(getattr(optimizer, "writes_shadows", lambda: False)())
 
     # ------------------------------------------------------------------ one step, eager or under capture
     def _run(self, vol, img, ratio_2d, noise, noise_2d, out):
@@ -94,7 +103,8 @@ class JointPretrainStep:
         self.reducer.backward(total)
         self.reducer.finish()
         self.optimizer.step(max_grad_norm=self.clip_grad)
-        self.model.shadows_current()
+        if self._opt_writes_shadows:
+            self.model.shadows_current()
         out["loss"].copy_(loss.detach())
         out["loss_all"].copy_(total.detach())
         out["frame_loss"].copy_(frame_loss)
@@ -133,12 +143,17 @@ class JointPretrainStep:
         keep_2d = len_keep_of(pe.input_size[1] * pe.input_size[2], mask_ratio_2d) if joint else None
         key = (vol_shape, tuple(sample_2d.shape) if joint else None, keep_2d, noise is not None, noise_2d is not None)
         ent = self._entries.get(key)
+        if ent is not None:
+            self._entries.move_to_end(key)
         if ent is None:
             tp = vol_shape[2] // self.model.patch_embed.t_patch_size
             out = {"loss": torch.zeros((), device=dev), "loss_2d": torch.zeros((), device=dev),
                    "loss_all": torch.zeros((), device=dev), "frame_loss": torch.zeros(vol_shape[0], tp, device=dev),
                    "grad_norm": torch.zeros((), device=dev)}
             ent = self._entries[key] = {"calls": 0, "graph": None, "out": out}
+            while len(self._entries) > self.max_graphs:        # evict the least recently used signature (graph + statics)
+                _, old = self._entries.popitem(last=False)
+                old.clear()
         out = ent["out"]
         if not self.use_graph or ent["calls"] < self.warm_steps:
             ent["calls"] += 1
@@ -155,7 +170,9 @@ class JointPretrainStep:
             self.optimizer.prepare(max_grad_norm=self.clip_grad)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):  # capture records, it does not execute
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(graph, pool=self._pool):  # capture records, it does not execute
                 self._run(st["vol"], st["img"], mask_ratio_2d, st["noise"], st["noise_2d"], out)
             ent["graph"] = graph
         else:

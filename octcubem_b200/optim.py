@@ -87,7 +87,10 @@ class FusedAdamW(torch.optim.Optimizer):
     def _table(self, gi, group):
         live = [p for p in group["params"] if p.grad is not None]
         shs = [self._shadows(p) if self._shadows is not None else None for p in live]
-        key = tuple((p.data_ptr(), p.grad.data_ptr(), 0 if sh is None else sh.data_ptr()) for p, sh in zip(live, shs))
+        def mom(p):  # load_state_dict() swaps the moment tensors: the chunk table must follow them
+            st = self.state.get(p)
+            return (st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()) if st and "exp_avg" in st else (0, 0)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), 0 if sh is None else sh.data_ptr()) + mom(p) for p, sh in zip(live, shs))
         ent = self._tables.get(gi)
         if ent is not None and ent[0] == key:
             return ent
@@ -103,6 +106,11 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            for t in (p, p.grad, st["exp_avg"], st["exp_avg_sq"]):
+                if t.data_ptr() % 16:
+                    raise RuntimeError("FusedAdamW: parameters, gradients and moments must be 16-byte aligned (float4 access)")
+            if sh is not None and sh.data_ptr() % 8:
+                raise RuntimeError("FusedAdamW: bf16 shadows must be 8-byte aligned")
             n = p.numel()
             for off in range(0, n, CHUNK):
                 rows.append((p.data_ptr() + 4 * off, p.grad.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off,
@@ -110,6 +118,8 @@ class FusedAdamW(torch.optim.Optimizer):
                              min(CHUNK, n - off)))
         dev = group["params"][0].device
         t = torch.tensor(rows, dtype=torch.int64).reshape(-1, 6).to(dev) if rows else None
+        # (the key was computed before the moments of a first step existed: store the one that matches the table)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), 0 if sh is None else sh.data_ptr()) + mom(p) for p, sh in zip(live, shs))
         ent = (key, t, len(rows))
         self._tables[gi] = ent
         return ent
@@ -225,6 +235,45 @@ class FusedAdamW(torch.optim.Optimizer):
             for p in touched:
                 self.state[p]["step"] += 1  # host mirror: exact for eager steps, the device clock is authoritative under replay
             torch._C._autograd._unsafe_set_version_counter(touched, [p._version + 1 for p in touched])
+
+    # ------------------------------------------------------------------ checkpoint / resume (misc.save_model / load_model)
+    def state_dict(self):
+        """torch.optim.Optimizer.state_dict() with the step count read back from the DEVICE clock: under CUDA-graph replay the
+        host mirror `state[p]['step']` does not advance, the clock is authoritative (one host sync, checkpoint time only)."""
+        if self.schedule is not None and self.clock is not None:
+            step, _ = self.clock_state()
+            for group in self.param_groups:
+                for p in group["params"]:
+                    st = self.state.get(p)
+                    if st and "step" in st:
+                        st["step"] = step
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Restores moments and step; the chunk tables / norm workspace are rebuilt on the next step (they hold the OLD moment
+        pointers) and the device clock restarts from the loaded step, so the cosine schedule and the bias corrections resume
+        where the checkpoint left them."""
+        super().load_state_dict(state_dict)
+        self._tables, self._norm_ws = {}, None
+        steps = {int(st["step"]) for st in self.state.values() if "step" in st}
+        if len(steps) > 1:
+            raise RuntimeError(f"FusedAdamW.load_state_dict: parameters disagree on the step count ({sorted(steps)})")
+        for st in self.state.values():
+            if "step" in st:
+                st["step"] = int(st["step"])            # torch's AdamW stores 0-d tensors; this optimizer counts in python ints
+        if self.schedule is not None and steps:
+            self.set_clock(steps.pop())
+
+    def set_clock(self, step: int):
+        """Positions the device clock: the NEXT step() is optimizer step `step + 1` (lr and bias corrections follow from it)."""
+        dev = next(p for g in self.param_groups for p in g["params"]).device
+        if self.clock is None:
+            self.clock = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.clock.copy_(torch.tensor([int(step), 0, 0, 0], dtype=torch.int32), non_blocking=False)
+
+    def writes_shadows(self) -> bool:
+        """True when step() also emits the bf16 weight shadows (constructed with `shadows=`)."""
+        return self._shadows is not None
 
     def clock_state(self):
         """(step, lr) read back from the device clock (synchronises; logging only, engine_pretrain.py:186-187)."""

@@ -14,6 +14,8 @@ Fixtures:
   toy_vit_step.npz   the encoder-only ViT (OCTCube/models_vit_st_flash_attn.py), toy size (E=64/2 heads, 12x64x64, B=2, 5 classes),
                      eval mode: "sep::" = separable pos + cls + global pool, "joint::" = joint pos table + cls read-out:
                      volume, dlogits, reference logits / embedding / last hidden state / every parameter gradient.
+  full_cfg1_grads.npz  ViT-L, 48x256x256, mask 0.9: reference loss + the norm of every parameter gradient + strided slices of 18
+                     gradient tensors, for the first volume alone (cfg-1) and for the batch of 8 (cfg-2) (only with --full-grads).
   full_cfg1.json     ViT-L, 1x48x256x256, mask 0.9 (BASELINE cfg-1): reference loss / mask sum / pred stats
                      for oracle.init_state_dict(seed 0) weights (only with --full; ~1 min).
 """
@@ -175,12 +177,78 @@ def gen_full():
     print(rec)
 
 
+GRAD_SLICE_TENSORS = ("pos_embed_spatial", "pos_embed_temporal", "cls_token", "patch_embed.proj.weight", "blocks.0.mixer.Wqkv.weight",
+                      "blocks.0.norm1.weight", "blocks.11.mlp.fc1.weight", "blocks.23.mlp.fc2.weight", "blocks.23.mixer.out_proj.bias",
+                      "norm.weight", "decoder_embed.weight", "mask_token", "decoder_pos_embed_spatial",
+                      "decoder_blocks.0.mixer.Wqkv.weight", "decoder_blocks.7.mlp.fc2.weight", "decoder_norm.bias",
+                      "decoder_pred.weight", "decoder_pred.bias")
+
+
+def grad_slice(t, n=4096):
+    """Fixed, size-independent sample of a gradient tensor: every (numel // n)-th element of the flattened tensor."""
+    f = t.reshape(-1)
+    return f[:: max(1, f.numel() // n)][:n]
+
+
+def gen_full_grads(batch=8):
+    """Reference GRADIENTS at production size (ViT-L, 48x256x256, mask 0.9, fp32 CPU): cfg-1 (the first volume alone) and a
+    batch of `batch` volumes (BASELINE cfg-2's batch).  The reference is run once per volume — its softmax(QK^T) at S = 4097
+    needs ~20 GB per volume — and the batch step is assembled from the per-volume steps: every volume masks the same number of
+    tokens, so the batch loss `(loss * mask).sum() / mask.sum()` (models...:664) is the mean of the per-volume losses and its
+    gradient the mean of theirs.  Stored: loss, frame losses, the norm of EVERY parameter gradient and fixed strided slices
+    (4096 elements) of GRAD_SLICE_TENSORS."""
+    cfg = O.MAEConfig(num_frames=48, pred_t_dim=48)
+    sd = O.init_state_dict(cfg, seed=0)
+    vols = O.synthetic_volume(batch, 48, 256, 256, seed=0)
+    noises = O.synthetic_noise(batch, cfg.t_grid * cfg.grid ** 2, seed=1)
+    m = R.build_reference(**cfg.ref_kwargs())
+    m.load_state_dict(sd, strict=True)
+    acc, losses, frames, msum = None, [], [], None
+    rec = {}
+    for i in range(batch):
+        out = R.run_reference(m, vols[i:i + 1], noises[i:i + 1], 0.9, frame_loss=True, force_stable_argsort=True, backward=True)
+        assert msum is None or float(out["mask"].sum()) == msum
+        msum = float(out["mask"].sum())
+        losses.append(float(out["loss"]))
+        frames.append(out["frame_losses"].detach().flatten())
+        g = {k: v.double() for k, v in out["grads"].items()}
+        if i == 0:
+            rec["b1::loss"] = np.float64(losses[0])
+            rec["b1::frame_losses"] = frames[0].numpy()
+            for k, v in g.items():
+                rec["b1::norm::" + k] = np.float64(v.norm())
+            for k in GRAD_SLICE_TENSORS:
+                rec["b1::slice::" + k] = grad_slice(g[k]).float().numpy()
+            acc = g
+        else:
+            for k in acc:
+                acc[k] += g[k]
+        print(f"volume {i}: loss {losses[-1]:.6f}", flush=True)
+        del out, g
+    tag = f"b{batch}::"
+    rec[tag + "loss"] = np.float64(sum(losses) / batch)
+    rec[tag + "frame_losses"] = torch.stack(frames).numpy()
+    for k, v in acc.items():
+        v = v / batch
+        rec[tag + "norm::" + k] = np.float64(v.norm())
+        if k in GRAD_SLICE_TENSORS:
+            rec[tag + "slice::" + k] = grad_slice(v).float().numpy()
+    rec["mask_sum_per_volume"] = np.float64(msum)
+    np.savez_compressed(os.path.join(GOLD, "full_cfg1_grads.npz"), **rec)
+    print("full_cfg1_grads.npz:", len(rec), "entries; batch loss", rec[tag + "loss"])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--full-grads", action="store_true", help="full_cfg1_grads.npz only (reference fwd+bwd at production size; ~10 min)")
     ap.add_argument("--only-2d", action="store_true", help="regenerate toy2d_step.npz only")
     ap.add_argument("--only-vit", action="store_true", help="regenerate toy_vit_step.npz only")
     a = ap.parse_args()
+    if a.full_grads:
+        torch.set_num_threads(os.cpu_count())
+        gen_full_grads()
+        sys.exit(0)
     if a.only_2d:
         gen_toy2d()
         sys.exit(0)

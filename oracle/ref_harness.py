@@ -60,7 +60,7 @@ def _install_stubs():
         def forward(self, x):
             return self.fc2(self.act(self.fc1(x)))
 
-    if "timm" not in sys.modules:
+    if getattr(sys.modules.get("timm"), "__file__", None) is None:  # absent, or a stub (ours / oracle.gpu_incumbent's): complete it
         mod("timm")
         mod("timm.models")
         mod("timm.layers", to_2tuple=to_2tuple)

@@ -325,6 +325,27 @@ def test_mse_loss_channel_last_2d(norm_pix, pdtype):
     assert float(loss_m) == float(loss) and bool((tok_m[mask.to(DEV) == 0] == 0).all())   # masked-only mode: same loss
 
 
+def test_mse_loss_many_frames_and_trailing_rows():
+    """More than 4096 (b, t') groups (the finish kernel's staging tile) and a prediction buffer with rows BEHIND the L tokens
+    (their gradient rows must be zero, their mask must not be read)."""
+    cfg = O.MAEConfig(input_size=8, patch_size=4, num_frames=16, pred_t_dim=16, t_patch_size=1)
+    B, L, P = 300, 16 * 4, 16                                                     # B * T' = 4800 groups of 4 tokens
+    g = torch.Generator().manual_seed(8)
+    imgs = O.synthetic_volume(B, 16, 8, 8, seed=5, zero_pad_frames=0)
+    pred_full = torch.randn(B, 1 + L + 3, P, generator=g)
+    mask = (torch.rand(B, L, generator=g) > 0.4).float()
+    pr = pred_full.clone().requires_grad_(True)
+    loss_ref, fl_ref = O.forward_loss(cfg, imgs, pr[:, 1:1 + L], mask, frame_loss=True)
+    loss_ref.backward()
+    pd = pred_full.to(DEV).requires_grad_(True)
+    loss, fl, _ = ops.MaskedMSELossFn.apply(imgs.to(DEV), pd, mask.to(DEV), 4, 1, 1, False, None)
+    assert abs(float(loss) - float(loss_ref)) < 5e-6 * abs(float(loss_ref))
+    assert rel(fl, fl_ref.detach()) < 1e-5
+    loss.backward()
+    assert rel(pd.grad, pr.grad) < 1e-5
+    assert float(pd.grad[:, 1 + L:].abs().max()) == 0.0 and float(pd.grad[:, 0].abs().max()) == 0.0
+
+
 def test_mse_loss_frame_index_select():
     # pred_t_dim != T: linspace index_select of models...:630-640
     cfg = O.MAEConfig(input_size=64, num_frames=12, pred_t_dim=6, t_patch_size=2)  # u = 1, T' = 6
@@ -389,8 +410,11 @@ def test_linear_and_mlp_functions_bf16():
 @pytest.mark.parametrize("compute,dtype,tol", [(OCT_F32, torch.float32, 2e-5), (OCT_BF16, torch.bfloat16, 8e-3)])
 # 1030 / 1060: the last 256-row CTA holds a single live Q tile and sweeps 9 kv tiles (run-ahead 2); 1160: two live Q tiles
 # and a short last kv tile; 1030 / 1160 also have an odd number of 64-query sub-tiles in the backward sweep
+# 4097 / 5121: the production decoder lengths of cfg-1/2 and cfg-3 (32*128+1 / 40*128+1: the single-live-row tail CTA);
+# (8,410,16,64) / (2,512,16,64): the encoder shapes; 385 / 449 = 3*128+1 / 3*128+65 per head dim (tail sub-tiles)
 @pytest.mark.parametrize("B,S,H,d", [(2, 77, 2, 32), (1, 300, 2, 64), (2, 512, 4, 64), (1, 1030, 3, 32), (1, 1060, 2, 32),
-                                     (1, 1160, 2, 32), (1, 1030, 1, 64)])
+                                     (1, 1160, 2, 32), (1, 1030, 1, 64), (1, 4097, 2, 32), (1, 5121, 2, 32), (8, 410, 16, 64),
+                                     (2, 512, 16, 64), (1, 385, 2, 32), (1, 449, 2, 32), (1, 385, 2, 64), (1, 449, 2, 64)])
 def test_attention(compute, dtype, tol, B, S, H, d):
     import math
     g = torch.Generator().manual_seed(S)
@@ -406,6 +430,34 @@ def test_attention(compute, dtype, tol, B, S, H, d):
     assert rel(out, o_ref.detach()) < tol
     out.backward(dout.to(DEV))
     assert rel(qd.grad, x.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("S", [4097, 5121])
+def test_attention_at_the_bench_shape(S):
+    """The exact launch that is 47 % of the step: B = 8, H = 16, d = 32, S = 4097 (cfg-1/2) and 5121 (cfg-3), forward and
+    backward, checked on a spread of (batch, head) pairs against an fp64 evaluation of the same bf16 inputs (torch on the
+    GPU is only the checker here)."""
+    import math
+    B, H, d = 8, 16, 32
+    g = torch.Generator().manual_seed(S)
+    qkv = (torch.randn(B, S, 3 * H * d, generator=g) * 0.7).bfloat16().to(DEV).requires_grad_(True)
+    dout = torch.randn(B, S, H * d, generator=g).bfloat16().to(DEV)
+    out = ops.AttnFn.apply(qkv, H, OCT_BF16)
+    out.backward(dout)
+    q5 = qkv.detach().view(B, S, 3, H, d)
+    worst_o = worst_g = 0.0
+    for b, h in ((0, 0), (3, 7), (7, 15), (5, 1)):
+        x = q5[b, :, :, h, :].double().clone().requires_grad_(True)          # [S, 3, d]
+        q, k, v = x.unbind(1)
+        p = torch.softmax(q @ k.t() / math.sqrt(d), -1)
+        o_ref = p @ v
+        (o_ref * dout[b, :, h * d:(h + 1) * d].double()).sum().backward()
+        worst_o = max(worst_o, rel(out[b, :, h * d:(h + 1) * d], o_ref.detach()))
+        worst_g = max(worst_g, rel(qkv.grad.view(B, S, 3, H, d)[b, :, :, h, :], x.grad))
+    print(f"S={S}: worst out rel {worst_o:.2e}, worst dqkv rel {worst_g:.2e}")
+    assert worst_o < 8e-3 and worst_g < 1.6e-2
+    # the tail row (query S-1 lives alone in the last 128-row tile) and the cls row
+    assert torch.isfinite(out).all() and torch.isfinite(qkv.grad).all()
 
 
 @pytest.mark.parametrize("B,T,HW,E,u", [(2, 6, 64, 64, 3), (1, 12, 256, 1024, 3), (2, 3, 128, 264, 3)])
@@ -515,6 +567,66 @@ def test_fused_adamw_device_clock_follows_the_cosine_schedule(use_graph):
         assert step == k and dev_lr == pytest.approx(lr, rel=1e-6, abs=1e-12)
         for (name, p), (_, r) in zip(net.named_parameters(), ref.named_parameters()):
             assert rel(p.detach(), r.detach()) < 2e-6, (k, name)
+
+
+def test_fused_adamw_checkpoint_resume_under_graph_replay():
+    """optimizer.state_dict() / load_state_dict() on the clocked (graph-replayed) path (the reference checkpoints through
+    misc.save_model -> optimizer.state_dict()): the step count comes from the DEVICE clock (the host mirror does not advance
+    under replay), a resumed optimizer continues the cosine schedule and the bias corrections where the checkpoint left them,
+    and its kernels follow the loaded moment tensors (not the ones the tables were built for)."""
+    from octcubem_b200 import optim
+    sched = optim.CosineSchedule(lr=2e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=4.0, epochs_per_step=0.5)
+
+    def make():
+        torch.manual_seed(11)
+        net = torch.nn.Sequential(torch.nn.Linear(33, 65), torch.nn.LayerNorm(65), torch.nn.Linear(65, 515)).to(DEV)
+        opt = optim.FusedAdamW(optim.add_weight_decay(net, 0.05), lr=1.0, betas=(0.9, 0.95), schedule=sched)
+        grads = [torch.zeros_like(p) for p in net.parameters()]
+        for p, g in zip(net.parameters(), grads):
+            p.grad = g
+        return net, opt, grads
+
+    def feed(grads, k):
+        gen = torch.Generator().manual_seed(100 + k)
+        for g in grads:
+            g.copy_(torch.randn(g.shape, generator=gen).to(DEV))
+
+    def graph_of(opt):
+        opt.prepare()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            opt.step()
+        return gr
+
+    # uninterrupted: 6 replayed steps
+    net_a, opt_a, grads_a = make()
+    gr = graph_of(opt_a)
+    for k in range(1, 7):
+        feed(grads_a, k)
+        gr.replay()
+    # interrupted after 3 steps: checkpoint, fresh objects, resume
+    net_b, opt_b, grads_b = make()
+    gr_b = graph_of(opt_b)
+    for k in range(1, 4):
+        feed(grads_b, k)
+        gr_b.replay()
+    ck_opt, ck_net = opt_b.state_dict(), {k: v.clone() for k, v in net_b.state_dict().items()}
+    assert all(int(st["step"]) == 3 for st in ck_opt["state"].values())              # read from the device clock
+    net_c, opt_c, grads_c = make()
+    net_c.load_state_dict(ck_net)
+    opt_c.prepare()                                                                  # tables exist BEFORE the load
+    opt_c.load_state_dict(ck_opt)
+    assert opt_c.clock_state()[0] == 3
+    gr_c = graph_of(opt_c)
+    for k in range(4, 7):
+        feed(grads_c, k)
+        gr_c.replay()
+    assert opt_c.clock_state()[0] == 6 and opt_c.clock_state()[1] == pytest.approx(sched.lr_at_step(6), rel=1e-6)
+    for (name, p), (_, q) in zip(net_a.named_parameters(), net_c.named_parameters()):
+        assert torch.equal(p.detach(), q.detach()), name
+    for pa, pc in zip(net_a.parameters(), net_c.parameters()):
+        assert torch.equal(opt_a.state[pa]["exp_avg_sq"], opt_c.state[pc]["exp_avg_sq"])
 
 
 def test_fused_adamw_grad_scale_and_errors():
