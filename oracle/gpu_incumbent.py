@@ -208,7 +208,7 @@ def bench_block(frames, img, batch, mask_ratio, device, timed, steps):
     for _ in range(2):
         one()
     eager_ms = timed(one, steps) / steps
-    graph_ms = None
+    graph_ms, graph_err = None, None
     try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -223,14 +223,20 @@ def bench_block(frames, img, batch, mask_ratio, device, timed, steps):
             graph.replay()
         graph_ms = timed(graph.replay, steps) / steps
         del graph
-    except Exception:  # noqa: BLE001
-        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        graph_err = f"{type(e).__name__}: {e}"[:200]
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
     out = {"what": "the reference's GPU stack on this box: flash_attn 2.8.3 Blocks (FA2 kernels) + cuBLASLt nn.Linear + cuDNN "
                    "nn.Conv3d + ATen elementwise under torch.autocast(bf16), same volumes / batch / mask ratio, forward + backward "
                    "(oracle/gpu_incumbent.py; none of this repository's kernels)",
            "attention": attn + ("" if ok else f" (flash_attn unusable here: {why})"),
            "eager_ms_per_step": eager_ms, "eager_volumes_per_s": batch / (eager_ms / 1e3),
            "graph_ms_per_step": graph_ms, "graph_volumes_per_s": None if graph_ms is None else batch / (graph_ms / 1e3)}
+    if graph_err:
+        out["graph_capture_failed"] = graph_err
     del m
     torch.cuda.empty_cache()
     if ok:
