@@ -225,6 +225,42 @@ int oct_adamw_step_clocked(const int64_t* table, int64_t n_chunks, const void* c
 int oct_grad_norm(const int64_t* table, int64_t n_chunks, float grad_scale, float max_norm, float* partial, float* out,
                   oct_stream_t stream);
 
+/* ---- contrastive step of OCTCube-IR (retinal-COEM/src/open_clip/model.py:661-683, loss.py:21-63,148-229) ----
+ * oct_l2norm_*: F.normalize(x, dim=-1) (model.py:663,667): y[b,:] = x[b,:] / max(||x[b,:]||_2, eps), y fp32, inv_norm [B]
+ * saved for the backward (its sign bit marks rows that hit the eps clamp); dx = inv_norm * (dy - y <dy, y>).
+ *
+ * oct_clip_loss_*: ClipLoss.forward in the recipe's configuration (local_loss, gather_with_grad, labels = arange(B) + B*rank):
+ *   loss = ( CE(scale * image  @ all_enface^T, labels) + CE(scale * enface @ all_image^T, labels) ) / 2
+ * with the feature all-gather (loss.py:51-52) and, in the backward, the reduce-scatter its autograd implies folded INTO the
+ * kernels: `peer_bufs` is a HOST array of `world` device pointers — entry s is rank s's exchange buffer
+ * (oct_clip_xchg_bytes(B, D) bytes, zero-initialised, peer-mapped on this device: oct_peer_* below or any symmetric-memory
+ * allocator).  The forward publishes this rank's features into its own buffer, raises an epoch flag on every peer and reads
+ * the peers' features over NVLink tile by tile as their flags arrive; the backward additionally reads the peers' log-sum-exp
+ * vectors and emits d image, d enface ([B,D] fp32) and d logit_scale — no collective is launched.  Every rank must call fwd
+ * (then optionally bwd) once per step in the same order.  `state`: oct_clip_state_bytes(B) bytes of zero-initialised device
+ * memory owned by the caller (device-resident epoch: the launches replay from a CUDA graph).  image / enface [B,D] fp32,
+ * L2-normalised; logit_scale / dloss / loss / d_scale: device scalars; D % 4 == 0, D <= 1024, world <= 64. */
+int oct_l2norm_fwd(const void* x, int x_dtype, float* y, float* inv_norm, int64_t B, int64_t D, float eps, oct_stream_t stream);
+int oct_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, void* dx, int dx_dtype, int64_t B, int64_t D,
+                   oct_stream_t stream);
+size_t oct_clip_xchg_bytes(int64_t B, int64_t D);
+size_t oct_clip_state_bytes(int64_t B);
+int oct_clip_loss_fwd(const float* image, const float* enface, const float* logit_scale, const void* const* peer_bufs, void* state,
+                      float* loss, int rank, int world, int64_t B, int64_t D, oct_stream_t stream);
+int oct_clip_loss_bwd(const float* image, const float* enface, const float* logit_scale, const float* dloss,
+                      const void* const* peer_bufs, void* state, float* d_image, float* d_enface, float* d_scale, int rank, int world,
+                      int64_t B, int64_t D, oct_stream_t stream);
+
+/* Peer-mapped device memory, one process per GPU (CUDA IPC; NVLink 5 / NVSwitch carries the loads and stores).  Set-up time
+ * only — these are the library's only allocating entry points.  oct_peer_alloc: zero-filled cudaMalloc; oct_peer_export: 64-byte
+ * handle (HOST memory) to hand to the other ranks by any host channel; oct_peer_open: maps a peer's allocation, returns its
+ * address in this process; oct_peer_close / oct_peer_free undo them. */
+int oct_peer_alloc(void** ptr, int64_t bytes);
+int oct_peer_free(void* ptr);
+int oct_peer_export(void* ptr, void* handle64);
+int oct_peer_open(const void* handle64, void** ptr);
+int oct_peer_close(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,17 @@ SIGNATURES = {
     "oct_adamw_clock_advance": (I, [P, F, F, F, F, F, F, F, P]),
     "oct_adamw_step_clocked": (I, [P, L, P, F, F, F, F, F, F, P, P]),
     "oct_grad_norm": (I, [P, L, F, F, P, P, P]),
+    "oct_l2norm_fwd": (I, [P, I, P, P, L, L, F, P]),
+    "oct_l2norm_bwd": (I, [P, P, P, P, I, L, L, P]),
+    "oct_clip_xchg_bytes": (Z, [L, L]),
+    "oct_clip_state_bytes": (Z, [L]),
+    "oct_clip_loss_fwd": (I, [P, P, P, P, P, P, I, I, L, L, P]),
+    "oct_clip_loss_bwd": (I, [P, P, P, P, P, P, P, P, P, I, I, L, L, P]),
+    "oct_peer_alloc": (I, [POINTER(c_void_p), L]),
+    "oct_peer_free": (I, [P]),
+    "oct_peer_export": (I, [P, P]),
+    "oct_peer_open": (I, [P, POINTER(c_void_p)]),
+    "oct_peer_close": (I, [P]),
 }
 
 _lib = None
