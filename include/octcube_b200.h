@@ -195,6 +195,18 @@ int oct_mean_pool_bwd(const void* dout, int dout_dtype, void* dx, int dx_dtype, 
 int oct_ingest_u8(const uint8_t* src, float* dst, const uint8_t* flip_t, const uint8_t* flip_w, int64_t B, int64_t T_src,
                   int64_t T, int64_t H, int64_t W, float divisor, oct_stream_t stream);
 
+/* CropForegroundd + Resized(trilinear) + RandFlipd of create_3d_transforms (PatientDataset_inhouse.py:56-63), per cube, on the
+ * device.  The loader first pads / centre-crops the cube to T_pad frames (:436-450); coordinates below are in that padded cube.
+ * oct_fg_bbox_u8: bounding box of the voxels > 0 (monai CropForegroundd, margin 0) -> box[6] = {t0,t1,h0,h1,w0,w1} (device ints,
+ * ends exclusive; t1 == -1 when the cube has no foreground).  oct_resize_trilinear_u8: dst [T,H,W] f32 <- the box (or the whole
+ * padded cube when box == NULL or empty) of src [T_src,H_src,W_src] u8 scaled by 1/divisor, resampled like
+ * F.interpolate(mode="trilinear", align_corners=False) (ATen's source-index rule and blend order), then flipped along the frame
+ * axis / the width when flip_t / flip_w != 0. */
+int oct_fg_bbox_u8(const uint8_t* src, int* box, int64_t T_src, int64_t H, int64_t W, int64_t T_pad, oct_stream_t stream);
+int oct_resize_trilinear_u8(const uint8_t* src, float* dst, const int* box, int64_t T_src, int64_t H_src, int64_t W_src,
+                            int64_t T_pad, int64_t T, int64_t H, int64_t W, int flip_t, int flip_w, float divisor,
+                            oct_stream_t stream);
+
 /* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
 int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);
 

@@ -58,6 +58,7 @@ class GradReducer:
         self._slot: Dict[int, tuple] = {}
         self._hooks = []
         self._order: List[str] = []   # order in which gradients became ready on the discovery step
+        self._seen = set()
         self._named = dict(model.named_parameters())
         self._sink_keys: List[int] = []
         self._discovering = True
@@ -125,7 +126,9 @@ class GradReducer:
     def _make_hook(self, name):
         def hook(p):
             if self._discovering:
-                self._order.append(name)
+                if name not in self._seen:                 # (an accumulation group visits every parameter once per micro-step)
+                    self._seen.add(name)
+                    self._order.append(name)
                 return
             slot = self._slot.get(id(p))
             if slot is None:
@@ -165,21 +168,22 @@ class GradReducer:
     def no_sync(self):
         """Micro-steps 1 .. k-1 of a gradient-accumulation group (the role of DistributedDataParallel.no_sync): gradients
         accumulate in the buckets, nothing is reduced, finish() is not called.  The LAST micro-step runs outside this context
-        and reduces the accumulated sums.  Use the same backward style (reducer.backward or loss.backward) for all of them;
-        the bucket-discovery step cannot be a micro-step."""
-        if self._discovering:
-            raise RuntimeError("GradReducer.no_sync(): run one ordinary step first (bucket discovery)")
+        and reduces the accumulated sums.  Use the same backward style (reducer.backward or loss.backward) for all of them.
+        During the bucket-discovery group the micro-steps accumulate in ordinary autograd gradients; finish() of the group's
+        last pass moves the sums into the freshly built buckets."""
         self._no_sync = True
         try:
             yield
         finally:
             self._no_sync = False
 
-    def backward(self, loss: torch.Tensor):
-        """loss.backward() with the gradient seeded at 1 / world: the summed gradients are DDP's averages as they leave the
-        collective.  Follow with finish() as usual."""
+    def backward(self, loss: torch.Tensor, scale: float = 1.0):
+        """loss.backward() with the gradient seeded at scale / world: the summed gradients are DDP's averages as they leave the
+        collective (`scale` = 1 / accum_iter folds the reference's `loss /= accum_iter`, engine_pretrain.py:163, into the seed).
+        Follow with finish() as usual."""
         self._prescaled = self.world > 1
-        loss.backward(gradient=torch.full_like(loss, 1.0 / self.world) if self.world > 1 else None)
+        seed = float(scale) / self.world
+        loss.backward(gradient=torch.full_like(loss, seed) if seed != 1.0 else None)
 
     def finish(self):
         """Call after loss.backward(): joins the communication stream; on the discovery step performs the (non-overlapped)
@@ -248,6 +252,7 @@ class GradReducer:
     def reset(self):
         self._clear_sinks()
         self.buckets, self._slot, self._order, self._discovering = None, {}, [], True
+        self._seen = set()
 
     def remove(self):
         self._clear_sinks()

@@ -71,13 +71,16 @@ class StepResult:
 class JointPretrainStep:
     def __init__(self, model, optimizer: FusedAdamW, mask_ratio: float = 0.9, clip_grad: Optional[float] = None,
                  accum_iter: int = 1, use_graph: bool = True, warm_steps: int = 2, process_group=None, max_graphs: int = 2):
-        if accum_iter != 1:
-            raise NotImplementedError("JointPretrainStep: accum_iter > 1 is not implemented (the reference recipe uses 1 per GPU batch)")
+        if int(accum_iter) < 1:
+            raise ValueError("accum_iter must be >= 1")
         if use_graph and optimizer.schedule is None:
             raise ValueError("JointPretrainStep(use_graph=True) needs FusedAdamW(schedule=CosineSchedule(...)): a host-side "
                              "learning rate / step count would be frozen into the captured graph")
         self.model, self.optimizer = model, optimizer
         self.mask_ratio, self.clip_grad = mask_ratio, clip_grad
+        # gradient accumulation (engine_pretrain.py:163-173): `loss /= accum_iter`, the optimizer (and, here, the gradient
+        # exchange) runs on every accum_iter-th call only, gradients are zeroed after it.  Calls are counted per object.
+        self.accum_iter, self._micro = int(accum_iter), 0
         self.use_graph, self.warm_steps = use_graph, max(2, int(warm_steps))  # bucket discovery + one bucketed step
         self.reducer = GradReducer(model, process_group)
         # graphs per input signature, least recently used first.  `mask_ratio_2d_scheduler` walks through ~100 keep counts
@@ -92,19 +95,24 @@ class JointPretrainStep:
         self._opt_writes_shadows = bool(getattr(optimizer, "writes_shadows", lambda: False)())
 
     # ------------------------------------------------------------------ one step, eager or under capture
-    def _run(self, vol, img, ratio_2d, noise, noise_2d, out):
-        self.reducer.zero_grad()
+    def _run(self, vol, img, ratio_2d, noise, noise_2d, out, first=True, last=True):
+        if first:
+            self.reducer.zero_grad()
         (loss, frame_loss), _, _ = self.model(vol, mask_ratio=self.mask_ratio, frame_loss=True, noise=noise)
         total = loss
         if img is not None:
             loss_2d, _, _ = self.model(img, mask_ratio=ratio_2d, noise=noise_2d)
             total = loss + loss_2d
             out["loss_2d"].copy_(loss_2d.detach())
-        self.reducer.backward(total)
-        self.reducer.finish()
-        self.optimizer.step(max_grad_norm=self.clip_grad)
-        if self._opt_writes_shadows:
-            self.model.shadows_current()
+        if last:
+            self.reducer.backward(total, scale=1.0 / self.accum_iter)
+            self.reducer.finish()
+            self.optimizer.step(max_grad_norm=self.clip_grad)
+            if self._opt_writes_shadows:
+                self.model.shadows_current()
+        else:
+            with self.reducer.no_sync():                       # a micro-step: the sums stay local, nothing is exchanged
+                self.reducer.backward(total, scale=1.0 / self.accum_iter)
         out["loss"].copy_(loss.detach())
         out["loss_all"].copy_(total.detach())
         out["frame_loss"].copy_(frame_loss)
@@ -141,7 +149,9 @@ class JointPretrainStep:
         dev = cube.device if cube is not None else samples.device
         pe = self.model.high_res_patch_embed if joint else None
         keep_2d = len_keep_of(pe.input_size[1] * pe.input_size[2], mask_ratio_2d) if joint else None
-        key = (vol_shape, tuple(sample_2d.shape) if joint else None, keep_2d, noise is not None, noise_2d is not None)
+        first, last = self._micro == 0, self._micro == self.accum_iter - 1
+        self._micro = (self._micro + 1) % self.accum_iter
+        key = (vol_shape, tuple(sample_2d.shape) if joint else None, keep_2d, noise is not None, noise_2d is not None, first, last)
         ent = self._entries.get(key)
         if ent is not None:
             self._entries.move_to_end(key)
@@ -151,7 +161,7 @@ class JointPretrainStep:
                    "loss_all": torch.zeros((), device=dev), "frame_loss": torch.zeros(vol_shape[0], tp, device=dev),
                    "grad_norm": torch.zeros((), device=dev)}
             ent = self._entries[key] = {"calls": 0, "graph": None, "out": out}
-            while len(self._entries) > self.max_graphs:        # evict the least recently used signature (graph + statics)
+            while len(self._entries) > self.max_graphs * min(self.accum_iter, 3):   # (one graph per micro-step phase)
                 _, old = self._entries.popitem(last=False)
                 old.clear()
         out = ent["out"]
@@ -159,7 +169,7 @@ class JointPretrainStep:
             ent["calls"] += 1
             if cube is not None:
                 samples = ops.ingest_u8(cube, vol_shape[2], flip_t=flip_t, flip_w=flip_w)
-            self._run(samples, sample_2d, mask_ratio_2d, noise, noise_2d, out)
+            self._run(samples, sample_2d, mask_ratio_2d, noise, noise_2d, out, first, last)
             return self._result(out, joint)
         if ent["graph"] is None:
             if cube is not None:
@@ -167,13 +177,14 @@ class JointPretrainStep:
             st = ent["static"] = {"vol": samples.clone(), "img": sample_2d.clone() if joint else None,
                                   "noise": noise.clone() if noise is not None else None,
                                   "noise_2d": noise_2d.clone() if noise_2d is not None else None}
-            self.optimizer.prepare(max_grad_norm=self.clip_grad)
+            if last:
+                self.optimizer.prepare(max_grad_norm=self.clip_grad)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
             with torch.cuda.graph(graph, pool=self._pool):  # capture records, it does not execute
-                self._run(st["vol"], st["img"], mask_ratio_2d, st["noise"], st["noise_2d"], out)
+                self._run(st["vol"], st["img"], mask_ratio_2d, st["noise"], st["noise_2d"], out, first, last)
             ent["graph"] = graph
         else:
             st = ent["static"]

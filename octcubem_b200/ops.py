@@ -114,6 +114,26 @@ def ingest_u8(cube_u8, T, out=None, flip_t=None, flip_w=None, divisor=255.0):
     return out
 
 
+def crop_resize_u8(cube_u8, T_pad, T, H, W, out=None, crop_foreground=True, flip_t=False, flip_w=False, divisor=255.0):
+    """One uint8 cube [T_src, H_src, W_src] -> fp32 [T, H, W]: the loader's centre pad / crop to T_pad frames, then
+    create_3d_transforms (PatientDataset_inhouse.py:56-63): CropForegroundd (bounding box of the voxels > 0; the train
+    transform only), Resized(spatial_size=(T, H, W), mode="trilinear"), RandFlipd over frames / width — on the device, from the
+    uint8 cube (ToTensor's /255 applied to the 8 corner voxels of every output voxel).  `out`: optional destination view."""
+    _chk(cube_u8, out)
+    assert cube_u8.dtype == torch.uint8 and cube_u8.dim() == 3
+    T_src, Hs, Ws = cube_u8.shape
+    if out is None:
+        out = torch.empty(T, H, W, dtype=torch.float32, device=cube_u8.device)
+    assert out.dtype == torch.float32 and out.numel() == T * H * W
+    box = None
+    if crop_foreground:
+        box = torch.empty(6, dtype=torch.int32, device=cube_u8.device)
+        _call("oct_fg_bbox_u8", _p(cube_u8), _p(box), T_src, Hs, Ws, T_pad, _stream())
+    _call("oct_resize_trilinear_u8", _p(cube_u8), _p(out), _p(box), T_src, Hs, Ws, T_pad, T, H, W, int(bool(flip_t)), int(bool(flip_w)),
+          float(divisor), _stream())
+    return out
+
+
 def gemm(layout, A, B, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, aux=None, out=None, beta=0, compute=None):
     """D[M,N] = op(A) op(B) (+ epilogue); see include/octcube_b200.h for the layouts.  A, B 2-D contiguous."""
     _chk(A, B, bias, aux, out)

@@ -104,5 +104,42 @@ def test_engine_refuses_a_host_side_schedule_under_graphs():
     m = build(sd, "fp32")
     with pytest.raises(ValueError, match="schedule"):
         JointPretrainStep(m, optim.FusedAdamW(optim.add_weight_decay(m, 0.05)), use_graph=True)
-    with pytest.raises(NotImplementedError):
-        JointPretrainStep(m, optim.FusedAdamW(optim.add_weight_decay(m, 0.05)), use_graph=False, accum_iter=2)
+    with pytest.raises(ValueError):
+        JointPretrainStep(m, optim.FusedAdamW(optim.add_weight_decay(m, 0.05)), use_graph=False, accum_iter=0)
+
+
+@pytest.mark.parametrize("accum", [2, 3])
+def test_gradient_accumulation_matches_the_reference_loop(accum):
+    """accum_iter > 1 (engine_pretrain.py:163-173): `loss /= accum_iter`, backward every call, optimizer + zero_grad on every
+    accum_iter-th call, the learning rate set at the first call of each group — against the eager torch loop.  Groups 1-2 run
+    eagerly (bucket discovery inside an accumulation group, then the in-place sinks accumulating), groups 3-4 replay one
+    captured graph per micro-step phase."""
+    sd, _, _ = toy_inputs()
+    sched = dict(lr=3e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=3.0)
+    eng_model, ref_model = build(sd, "fp32"), build(sd, "fp32")
+    opt = optim.FusedAdamW(optim.add_weight_decay(eng_model, 0.05), betas=(0.9, 0.95),
+                           schedule=optim.CosineSchedule(**sched, epochs_per_step=0.5))
+    engine = JointPretrainStep(eng_model, opt, mask_ratio=0.9, clip_grad=0.5, use_graph=True, warm_steps=2, accum_iter=accum)
+    ropt = torch.optim.AdamW(optim.add_weight_decay(ref_model, 0.05), lr=1.0, betas=(0.9, 0.95))
+    try:
+        it = 0
+        for group in range(1, 5):
+            optim.adjust_learning_rate(ropt, (group - 1) * 0.5, sched["lr"], sched["min_lr"], sched["warmup_epochs"], sched["epochs"])
+            for micro in range(accum):
+                it += 1
+                vol = O.synthetic_volume(2, 12, 64, 64, seed=10 + it, zero_pad_frames=1).to(DEV)
+                noise = O.synthetic_noise(2, 64, seed=20 + it).to(DEV)
+                res = engine(vol, noise=noise)
+                (loss, fl), _, _ = ref_model(vol, mask_ratio=0.9, frame_loss=True, noise=noise)
+                (loss / accum).backward()
+                assert float(res.loss) == pytest.approx(float(loss.detach()), rel=2e-4), (group, micro)
+            norm = torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.5)
+            ropt.step()
+            ropt.zero_grad(set_to_none=True)
+            assert float(res.grad_norm) == pytest.approx(float(norm), rel=1e-3), group
+            for (name, p), (_, r) in zip(eng_model.named_parameters(), ref_model.named_parameters()):
+                assert rel(p.detach(), r.detach()) < 1e-3, (group, name)
+        assert opt.clock_state()[0] == 4                                     # one optimizer step per group
+        assert all(e["graph"] is not None for e in engine._entries.values())
+    finally:
+        engine.close()

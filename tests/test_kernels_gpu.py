@@ -277,6 +277,48 @@ def test_ingest_u8_bit_exact(B, T_src, T, H, W):
     assert torch.equal(ops.ingest_u8(cube.to(DEV), T).cpu(), _cpu_ingest(cube, T, None, None))     # no flips
 
 
+def _cpu_crop_resize(cube, T_pad, T, H, W, crop, flip_t, flip_w, device="cpu"):
+    """The loader's CPU pipeline (PatientDataset_inhouse.py:420-450 + create_3d_transforms :56-63) restated with torch:
+    ToTensor, centre pad / crop of frames, monai CropForegroundd (box of x > 0, margin 0), Resized = F.interpolate trilinear."""
+    fr = cube.float() / 255.0
+    n = fr.shape[0]
+    if n < T_pad:
+        left = (T_pad - n) // 2
+        fr = torch.cat([torch.zeros(left, *fr.shape[1:]), fr, torch.zeros(T_pad - n - left, *fr.shape[1:])], 0)
+    elif n > T_pad:
+        left = (n - T_pad) // 2
+        fr = fr[left:left + T_pad]
+    if crop and bool((fr > 0).any()):
+        nz = fr > 0
+        idx = [nz.any(dim=tuple(d for d in range(3) if d != a)).nonzero().flatten() for a in range(3)]
+        fr = fr[idx[0][0]:idx[0][-1] + 1, idx[1][0]:idx[1][-1] + 1, idx[2][0]:idx[2][-1] + 1]
+    out = F.interpolate(fr[None, None].to(device), size=(T, H, W), mode="trilinear", align_corners=False)[0, 0]
+    if flip_t:
+        out = out.flip(0)
+    if flip_w:
+        out = out.flip(2)
+    return out
+
+
+@pytest.mark.parametrize("T_src,Hs,Ws,T_pad,T,H,W,crop", [(49, 96, 128, 60, 60, 64, 64, True), (61, 64, 256, 48, 48, 32, 96, True),
+                                                          (25, 40, 64, 25, 60, 256, 256, False), (30, 48, 64, 40, 20, 24, 32, True)])
+def test_crop_resize_trilinear_vs_interpolate(T_src, Hs, Ws, T_pad, T, H, W, crop):
+    """CropForegroundd + Resized(trilinear) + flips on the device from the uint8 cube vs F.interpolate on the CPU (what the
+    reference's loader runs) and on the GPU (the blend order the kernel follows).  fp32 blends of 8 corners: a few ulp."""
+    g = torch.Generator().manual_seed(T_src)
+    cube = torch.randint(0, 256, (T_src, Hs, Ws), generator=g, dtype=torch.uint8)
+    cube[:3] = 0; cube[-2:] = 0; cube[:, :5] = 0; cube[:, -7:] = 0; cube[:, :, :9] = 0; cube[:, :, -4:] = 0   # a foreground box
+    for ft, fw in ((False, False), (True, True)):
+        got = ops.crop_resize_u8(cube.to(DEV), T_pad, T, H, W, crop_foreground=crop, flip_t=ft, flip_w=fw).cpu()
+        ref_cpu = _cpu_crop_resize(cube, T_pad, T, H, W, crop, ft, fw)
+        ref_gpu = _cpu_crop_resize(cube, T_pad, T, H, W, crop, ft, fw, device=DEV).cpu()
+        assert got.shape == ref_cpu.shape
+        assert float((got - ref_cpu).abs().max()) < 1e-6 and float((got - ref_gpu).abs().max()) < 1e-6
+        print("bit-equal to F.interpolate on CUDA:", bool(torch.equal(got, ref_gpu)), " on CPU:", bool(torch.equal(got, ref_cpu)))
+    empty = torch.zeros(T_src, Hs, Ws, dtype=torch.uint8)                   # no foreground: the whole (padded) cube is resampled
+    assert float(ops.crop_resize_u8(empty.to(DEV), T_pad, T, H, W).abs().max()) == 0.0
+
+
 # ---------------------------------------------------------------- loss
 @pytest.mark.parametrize("norm_pix", [False, True])
 @pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
