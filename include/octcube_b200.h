@@ -51,6 +51,12 @@ const char* oct_version(void);
 const char* oct_last_error(void);
 /* number of kernels this library has launched in this process so far (evidence for bench.py's gpu_launches) */
 uint64_t oct_launch_count(void);
+/* Programmatic dependent launch for the launches that follow (process-wide): 1 = the hot kernels are launched with the
+ * programmatic-stream-serialization attribute (their prologues — barrier init, TMEM allocation, tensor-map prefetch — overlap
+ * the tail of the previous kernel; every kernel executes griddepcontrol.wait before touching memory), 0 = off, -1 = follow the
+ * OCT_PDL environment variable (default off).  The module turns it on for the FORWARD pass only: in the backward pass early-
+ * resident CTAs of the dgrad chain would take the SMs the side-stream weight-gradient GEMMs fill. */
+void oct_set_pdl(int mode);
 /* sm_count / compute capability of the current device; returns OCT_ERR_UNSUPPORTED unless cc == 10.x */
 int oct_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -83,6 +89,13 @@ int oct_patch_embed_fwd(const float* imgs, const float* weight, const float* bia
 int oct_gather_tokens_fwd(const void* x, int x_dtype, const int64_t* ids_keep, const float* pos_sp, const float* pos_tmp,
                           const float* cls_row, float* out, int64_t B, int64_t L, int64_t keep, int64_t G, int64_t C,
                           oct_stream_t stream);
+/* Same output as oct_gather_tokens_fwd for an x that holds the kept rows only (x_keep [B,keep,C], the gather-first patch
+ * embedding: patchify the kept tokens, one GEMM over B*keep rows): out[b,0] = cls_row, out[b,1+i] = x_keep[b,i] +
+ * pos_sp[ids_keep[b,i] % G] + pos_tmp[ids_keep[b,i] / G]. */
+int oct_posadd_tokens_fwd(const void* x_keep, int x_dtype, const int64_t* ids_keep, const float* pos_sp, const float* pos_tmp,
+                          const float* cls_row, float* out, int64_t B, int64_t L, int64_t keep, int64_t G, int64_t C,
+                          oct_stream_t stream);
+
 /* backward: dx_keep [B*keep, C] (f32|bf16) = dout rows 1.. ; d_pos_sp [G,C], d_pos_tmp [L/G,C], d_cls_row [C] are
  * deterministic segmented sums (overwritten). */
 int oct_gather_tokens_bwd(const float* dout, const int64_t* ids_keep, void* dx_keep, int dx_dtype, float* d_pos_sp,
@@ -102,6 +115,12 @@ size_t oct_add_ln_bwd_ws_bytes(int64_t M, int64_t C);
 int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                    const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, int dx_lp_dtype, float* dgamma,
                    float* dbeta, void* ws, size_t ws_bytes, int64_t M, int64_t C, oct_stream_t stream);
+/* oct_add_ln_bwd in two launches: `main` writes dx and leaves per-CTA partial sums of dgamma / dbeta in ws (*nblocks = number of
+ * partial rows, a HOST int), `finish` reduces them in a fixed order — on any stream, e.g. off the dgrad chain. */
+int oct_add_ln_bwd_main(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, int dx_lp_dtype, void* ws,
+                        size_t ws_bytes, int64_t M, int64_t C, int* nblocks, oct_stream_t stream);
+int oct_add_ln_bwd_finish(const void* ws, int nblocks, int64_t C, float* dgamma, float* dbeta, oct_stream_t stream);
 
 /* ---- GEMM (replaces cuBLASLt for Wqkv/out_proj/fc1/fc2/decoder_embed/decoder_pred and their dgrad/wgrad) ----
  * compute = OCT_BF16: A,B bf16, tcgen05.mma kind::f16, fp32 accumulate in TMEM, TMA-fed; D bf16|f32.
@@ -262,6 +281,22 @@ int oct_clip_loss_fwd(const float* image, const float* enface, const float* logi
 int oct_clip_loss_bwd(const float* image, const float* enface, const float* logit_scale, const float* dloss,
                       const void* const* peer_bufs, void* state, float* d_image, float* d_enface, float* d_scale, int rank, int world,
                       int64_t B, int64_t D, oct_stream_t stream);
+
+/* ---- gradient all-reduce over NVLink / NVSwitch without a collective library (the all-reduce behind
+ * DistributedDataParallel, main_pretrain...:435-439) ----------------------------------------------------------------------
+ * In-place SUM (times `scale`) of n_elems fp32 values at element offset off_elems of a SYMMETRIC buffer: every rank holds one
+ * copy of the allocation, all copies are mapped into every process (peer_bufs: HOST array [world] of device pointers, entry s =
+ * rank s's copy) and, on NVSwitch fabrics, behind ONE multicast address mc_ptr (NULL selects the peer path).  Multicast path:
+ * rank r reduces its 1/world shard with multimem.ld_reduce (the switch adds the copies) and broadcasts it with multimem.st; peer
+ * path: the same two-shot schedule with peer loads / stores.  Ranks synchronise through epoch flags inside the allocation
+ * (flag_off_bytes: oct_allreduce_flag_bytes() zero-initialised bytes at the same offset in every copy); `state`: local device
+ * memory (oct_allreduce_state_bytes(), zero-initialised; word 2 of slot `slot` is raised if a peer never arrived).  The kernel
+ * uses no shared memory, so its CTAs co-reside with the persistent GEMM / attention CTAs of the backward pass it overlaps.
+ * Every rank issues the same sequence of calls; calls in flight at the same time use different slots (0..7). */
+size_t oct_allreduce_flag_bytes(void);
+size_t oct_allreduce_state_bytes(void);
+int oct_allreduce_sym(void* mc_ptr, const void* const* peer_bufs, int64_t flag_off_bytes, void* state, int64_t off_elems,
+                      int64_t n_elems, int rank, int world, int slot, float scale, int ctas, oct_stream_t stream);
 
 /* Peer-mapped device memory, one process per GPU (CUDA IPC; NVLink 5 / NVSwitch carries the loads and stores).  Set-up time
  * only — these are the library's only allocating entry points.  oct_peer_alloc: zero-filled cudaMalloc; oct_peer_export: 64-byte

@@ -25,15 +25,19 @@ SIGNATURES = {
     "oct_version": (c_char_p, []),
     "oct_last_error": (c_char_p, []),
     "oct_launch_count": (ctypes.c_uint64, []),
+    "oct_set_pdl": (None, [I]),
     "oct_device_info": (I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "oct_mask_sort": (I, [P, L, L, L, P, P, P, P]),
     "oct_patchify": (I, [P, P, I, P, P, L, L, L, L, L, L, L, L, P]),
     "oct_patch_embed_fwd": (I, [P, P, P, P, I, L, L, L, L, L, L, L, P]),
     "oct_gather_tokens_fwd": (I, [P, I, P, P, P, P, P, L, L, L, L, L, P]),
+    "oct_posadd_tokens_fwd": (I, [P, I, P, P, P, P, P, L, L, L, L, L, P]),
     "oct_gather_tokens_bwd": (I, [P, P, P, I, P, P, P, L, L, L, L, L, P]),
     "oct_add_ln_fwd": (I, [P, I, P, P, P, P, P, I, P, P, L, L, F, P]),
     "oct_add_ln_bwd_ws_bytes": (Z, [L, L]),
     "oct_add_ln_bwd": (I, [P, I, P, I, P, P, P, P, P, P, I, P, P, P, Z, L, L, P]),
+    "oct_add_ln_bwd_main": (I, [P, I, P, I, P, P, P, P, P, P, I, P, Z, L, L, POINTER(c_int), P]),
+    "oct_add_ln_bwd_finish": (I, [P, I, L, P, P, P]),
     "oct_gemm": (I, [I, I, P, P, P, I, L, L, L, L, L, L, I, P, P, I, P]),
     "oct_gemm_wgrad_bias": (I, [I, P, P, P, P, L, L, L, L, L, L, I, P]),
     "oct_attn_fwd": (I, [I, P, P, P, L, L, L, L, F, P]),
@@ -65,6 +69,9 @@ SIGNATURES = {
     "oct_clip_state_bytes": (Z, [L]),
     "oct_clip_loss_fwd": (I, [P, P, P, P, P, P, I, I, L, L, P]),
     "oct_clip_loss_bwd": (I, [P, P, P, P, P, P, P, P, P, I, I, L, L, P]),
+    "oct_allreduce_flag_bytes": (Z, []),
+    "oct_allreduce_state_bytes": (Z, []),
+    "oct_allreduce_sym": (I, [P, P, L, P, L, L, I, I, I, F, I, P]),
     "oct_peer_alloc": (I, [POINTER(c_void_p), L]),
     "oct_peer_free": (I, [P]),
     "oct_peer_export": (I, [P, P]),

@@ -24,11 +24,17 @@ int oct_check_launch(const char* what) {
   return OCT_OK;
 }
 
+static int g_pdl_override = -1;  // oct_set_pdl(): -1 = follow the OCT_PDL environment variable
+
 bool oct_pdl_enabled() {
+  const int ov = __atomic_load_n(&g_pdl_override, __ATOMIC_RELAXED);
+  if (ov >= 0) return ov != 0;
   static int on = -1;
   if (on < 0) { const char* e = getenv("OCT_PDL"); on = (e && e[0] == '1') ? 1 : 0; }  // opt-in: see common.cuh
   return on != 0;
 }
+
+extern "C" void oct_set_pdl(int mode) { __atomic_store_n(&g_pdl_override, mode < 0 ? -1 : (mode ? 1 : 0), __ATOMIC_RELAXED); }
 
 int oct_num_sms() {
   static thread_local int cached_dev = -1, cached = 0;

@@ -359,7 +359,7 @@ extern "C" size_t oct_add_ln_bwd_ws_bytes(int64_t M, int64_t C) {
 template <int NV, typename TDY, typename TX, typename TLP>
 static int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                          const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma, float* dbeta, float* ws,
-                         int64_t M, int C, cudaStream_t st) {
+                         int64_t M, int C, cudaStream_t st, int* nblocks_out = nullptr) {
   const int64_t blocks = ln_bwd_blocks(M);
   const size_t smem = (size_t)kLnWarps * 2 * C * sizeof(float);
   auto kern = add_ln_bwd_kernel<NV, TDY, TX, TLP>;
@@ -371,6 +371,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* mean, const
                                                      (TLP*)dx_lp, ws, M, C);
   int rc = oct_check_launch("oct_add_ln_bwd");
   if (rc) return rc;
+  if (nblocks_out) { *nblocks_out = (int)blocks; return OCT_OK; }  // the caller runs the finish (another stream)
   ln_bwd_finish_kernel<<<(unsigned)ceil_div64(2 * C, 32), dim3(32, 32), 0, st>>>(ws, dgamma, dbeta, (int)blocks, C);
   return oct_check_launch("oct_add_ln_bwd(finish)");
 }
@@ -378,7 +379,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* mean, const
 template <int NV, int WPR>
 static int launch_ln_bwd_pipe_t(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                                 const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma,
-                                float* dbeta, float* ws, int64_t M, cudaStream_t st) {
+                                float* dbeta, float* ws, int64_t M, cudaStream_t st, int* nblocks_out) {
   constexpr int C = 128 * NV * WPR, kTeams = kLnWarps / WPR;
   int64_t blocks = ceil_div64(M, kTeams);
   const int64_t cap = (int64_t)oct_num_sms() * 3;  // ~150 registers per thread: three CTAs per SM
@@ -394,6 +395,7 @@ static int launch_ln_bwd_pipe_t(const void* dy, int dy_dtype, const void* x, int
 #undef LNP
   int rc = oct_check_launch("oct_add_ln_bwd(pipe)");
   if (rc) return rc;
+  if (nblocks_out) { *nblocks_out = (int)blocks; return OCT_OK; }
   oct_launch(ln_bwd_finish_kernel, dim3((unsigned)ceil_div64(2 * C, 32)), dim3(32, 32), 0, st, 1, (const float*)ws, dgamma, dbeta,
              (int)blocks, C);
   return oct_check_launch("oct_add_ln_bwd(finish)");
@@ -401,8 +403,8 @@ static int launch_ln_bwd_pipe_t(const void* dy, int dy_dtype, const void* x, int
 
 static int launch_ln_bwd_pipe(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                               const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma,
-                              float* dbeta, float* ws, int64_t M, int C, cudaStream_t st) {
-#define A dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, ws, M, st
+                              float* dbeta, float* ws, int64_t M, int C, cudaStream_t st, int* nblocks_out) {
+#define A dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, ws, M, st, nblocks_out
   switch (C) {
     case 128: return launch_ln_bwd_pipe_t<1, 1>(A);
     case 256: return launch_ln_bwd_pipe_t<2, 1>(A);
@@ -416,8 +418,8 @@ static int launch_ln_bwd_pipe(const void* dy, int dy_dtype, const void* x, int x
 template <typename TDY, typename TX, typename TLP>
 static int dispatch_ln_bwd_nv(int nv, const void* dy, const void* x, const float* mean, const float* rstd,
                               const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp, float* dgamma,
-                              float* dbeta, float* ws, int64_t M, int C, cudaStream_t st) {
-#define A dy, x, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, ws, M, C, st
+                              float* dbeta, float* ws, int64_t M, int C, cudaStream_t st, int* nblocks_out) {
+#define A dy, x, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, ws, M, C, st, nblocks_out
   switch (nv) {
     case 1: return launch_ln_bwd<1, TDY, TX, TLP>(A);
     case 2: return launch_ln_bwd<2, TDY, TX, TLP>(A);
@@ -428,11 +430,11 @@ static int dispatch_ln_bwd_nv(int nv, const void* dy, const void* x, const float
 #undef A
 }
 
-extern "C" int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean,
+static int add_ln_bwd_impl(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean,
                               const float* rstd, const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp,
                               int dx_lp_dtype, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int64_t M,
-                              int64_t C, oct_stream_t stream) {
-  OCT_REQUIRE(dy && x && mean && rstd && gamma && dgamma && dbeta, "oct_add_ln_bwd: null pointer");
+                              int64_t C, oct_stream_t stream, int* nblocks_out) {
+  OCT_REQUIRE(dy && x && mean && rstd && gamma && (nblocks_out || (dgamma && dbeta)), "oct_add_ln_bwd: null pointer");
   OCT_REQUIRE(C > 0 && C % 4 == 0 && C <= 2048, "oct_add_ln_bwd: need C%%4==0 and C<=2048 (got %lld)", (long long)C);
   if (!ws || ws_bytes < oct_add_ln_bwd_ws_bytes(M, C)) {
     oct_set_error("oct_add_ln_bwd: workspace too small (%zu < %zu)", ws_bytes, oct_add_ln_bwd_ws_bytes(M, C));
@@ -440,6 +442,7 @@ extern "C" int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) {
+    if (nblocks_out) { *nblocks_out = 0; return OCT_OK; }
     cudaMemsetAsync(dgamma, 0, C * sizeof(float), st);
     cudaMemsetAsync(dbeta, 0, C * sizeof(float), st);
     return OCT_OK;
@@ -449,10 +452,10 @@ extern "C" int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x
   OCT_REQUIRE(!dx_lp || dx_lp_dtype == OCT_BF16, "oct_add_ln_bwd: dx_lp must be bf16");
   if (getenv("OCT_LN_NO_PIPE") == nullptr) {
     const int rc = launch_ln_bwd_pipe(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta,
-                                      (float*)ws, M, (int)C, st);
+                                      (float*)ws, M, (int)C, st, nblocks_out);
     if (rc != OCT_ERR_UNSUPPORTED) return rc;  // widths the pipelined kernel does not cover fall through
   }
-#define A nv, dy, x, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, (float*)ws, M, (int)C, st
+#define A nv, dy, x, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dgamma, dbeta, (float*)ws, M, (int)C, st, nblocks_out
   if (dy_dtype == OCT_F32 && x_dtype == OCT_F32) return dispatch_ln_bwd_nv<float, float, __nv_bfloat16>(A);
   if (dy_dtype == OCT_BF16 && x_dtype == OCT_F32) return dispatch_ln_bwd_nv<__nv_bfloat16, float, __nv_bfloat16>(A);
   if (dy_dtype == OCT_F32 && x_dtype == OCT_BF16) return dispatch_ln_bwd_nv<float, __nv_bfloat16, __nv_bfloat16>(A);
@@ -460,6 +463,38 @@ extern "C" int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x
     return dispatch_ln_bwd_nv<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(A);
 #undef A
   OCT_REQUIRE(false, "oct_add_ln_bwd: bad dtype");
+}
+
+extern "C" int oct_add_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean,
+                              const float* rstd, const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp,
+                              int dx_lp_dtype, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int64_t M,
+                              int64_t C, oct_stream_t stream) {
+  return add_ln_bwd_impl(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dx_lp_dtype, dgamma, dbeta, ws,
+                         ws_bytes, M, C, stream, nullptr);
+}
+
+// The same backward split in two launches for callers that keep the parameter-gradient reduction OFF the dgrad chain: `main`
+// writes dx (+ per-CTA partial sums of dgamma / dbeta into ws) and returns the number of partial rows; `finish` reduces them in a
+// fixed order on whatever stream the caller likes (the weight-gradient side stream in ops.AddLNFn).
+extern "C" int oct_add_ln_bwd_main(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean,
+                                   const float* rstd, const float* gamma, const float* dres_in, float* dx_f32, void* dx_lp,
+                                   int dx_lp_dtype, void* ws, size_t ws_bytes, int64_t M, int64_t C, int* nblocks,
+                                   oct_stream_t stream) {
+  OCT_REQUIRE(nblocks, "oct_add_ln_bwd_main: null nblocks");
+  return add_ln_bwd_impl(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres_in, dx_f32, dx_lp, dx_lp_dtype, nullptr, nullptr, ws,
+                         ws_bytes, M, C, stream, nblocks);
+}
+
+extern "C" int oct_add_ln_bwd_finish(const void* ws, int nblocks, int64_t C, float* dgamma, float* dbeta, oct_stream_t stream) {
+  OCT_REQUIRE(dgamma && dbeta && (ws || nblocks == 0) && C > 0 && nblocks >= 0, "oct_add_ln_bwd_finish: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nblocks == 0) {
+    cudaMemsetAsync(dgamma, 0, C * sizeof(float), st);
+    cudaMemsetAsync(dbeta, 0, C * sizeof(float), st);
+    return OCT_OK;
+  }
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div64(2 * C, 32), dim3(32, 32), 0, st>>>((const float*)ws, dgamma, dbeta, nblocks, (int)C);
+  return oct_check_launch("oct_add_ln_bwd_finish");
 }
 
 // ------------------------------------------------------------------------------------------------

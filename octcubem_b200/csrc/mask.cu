@@ -130,7 +130,9 @@ extern "C" int oct_patchify(const float* imgs, void* out, int out_dtype, const i
 // ------------------------------------------------------------------------------------------------
 // gather_tokens forward: one CTA per output row
 // ------------------------------------------------------------------------------------------------
-template <typename TX>
+// kGathered: x holds the kept rows only ([B, keep, C], e.g. the gather-first patch embedding) — ids_keep then selects the
+// positional rows, not the x row.
+template <typename TX, bool kGathered = false>
 __global__ void gather_tokens_fwd_kernel(const TX* __restrict__ x, const int64_t* __restrict__ ids_keep,
                                          const float* __restrict__ pos_sp, const float* __restrict__ pos_tmp,
                                          const float* __restrict__ cls_row, float* __restrict__ out, int L, int keep,
@@ -145,7 +147,7 @@ __global__ void gather_tokens_fwd_kernel(const TX* __restrict__ x, const int64_t
   }
   const int tok = (int)ids_keep[(size_t)b * keep + (r - has_cls)];
   const int t = tok / G, s = tok - t * G;
-  const TX* xr = x + ((size_t)b * L + tok) * C;
+  const TX* xr = kGathered ? x + ((size_t)b * keep + (r - has_cls)) * C : x + ((size_t)b * L + tok) * C;
   for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
     float4 v = Vec4<TX>::ld(xr + c);
     if (pos_sp) {
@@ -181,6 +183,28 @@ extern "C" int oct_gather_tokens_fwd(const void* x, int x_dtype, const int64_t* 
   else
     OCT_REQUIRE(false, "oct_gather_tokens_fwd: bad dtype");
   return oct_check_launch("oct_gather_tokens_fwd");
+}
+
+// x_keep [B, keep, C] (rows already gathered) + cls row + positional rows selected by ids_keep -> out [B, keep (+1), C] f32
+extern "C" int oct_posadd_tokens_fwd(const void* x_keep, int x_dtype, const int64_t* ids_keep, const float* pos_sp,
+                                     const float* pos_tmp, const float* cls_row, float* out, int64_t B, int64_t L,
+                                     int64_t keep, int64_t G, int64_t C, oct_stream_t stream) {
+  OCT_REQUIRE(x_keep && ids_keep && out && pos_sp, "oct_posadd_tokens_fwd: null pointer");
+  OCT_REQUIRE(C % 4 == 0 && G > 0 && L % G == 0, "oct_posadd_tokens_fwd: need C%%4==0 and L%%G==0");
+  OCT_REQUIRE(pos_tmp || L == G, "oct_posadd_tokens_fwd: pos_tmp may be NULL only when T'==1");
+  const int has_cls = cls_row ? 1 : 0;
+  if (B == 0 || keep + has_cls == 0) return OCT_OK;
+  dim3 grid((unsigned)(keep + has_cls), (unsigned)B);
+  const int threads = (int)((C / 4 < 256) ? ((C / 4 + 31) / 32 * 32) : 256);
+  if (x_dtype == OCT_F32)
+    gather_tokens_fwd_kernel<float, true><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        (const float*)x_keep, ids_keep, pos_sp, pos_tmp, cls_row, out, (int)L, (int)keep, (int)G, (int)C, has_cls);
+  else if (x_dtype == OCT_BF16)
+    gather_tokens_fwd_kernel<__nv_bfloat16, true><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_keep, ids_keep, pos_sp, pos_tmp, cls_row, out, (int)L, (int)keep, (int)G, (int)C, has_cls);
+  else
+    OCT_REQUIRE(false, "oct_posadd_tokens_fwd: bad dtype");
+  return oct_check_launch("oct_posadd_tokens_fwd");
 }
 
 // backward part 1: dx_keep rows (plain copy/cast of dout rows 1..)

@@ -29,7 +29,11 @@ import torch.distributed as dist
 class _Bucket:
     ALIGN = 32  # elements (fp32): 128 bytes
 
-    def __init__(self, params: List[torch.nn.Parameter], names: List[str], device, dtype):
+    @classmethod
+    def padded_numel(cls, params):
+        return sum(-(-p.numel() // cls.ALIGN) * cls.ALIGN for p in params)
+
+    def __init__(self, params: List[torch.nn.Parameter], names: List[str], device, dtype, flat=None, arena_off=0):
         self.params, self.names = params, names
         # every view starts on a 128-byte boundary: the optimizer / grad-norm kernels use float4 accesses on `param.grad` and
         # the wgrad kernels reach the views through TMA (16-byte alignment), whatever the numel of the tensors in front
@@ -38,7 +42,9 @@ class _Bucket:
             offs.append(off)
             off += -(-p.numel() // self.ALIGN) * self.ALIGN
         self.numel = off
-        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)   # (padding stays zero: a SUM all-reduce keeps it zero)
+        # `flat`: a slice of the reducer's symmetric arena (element offset arena_off), else an ordinary tensor
+        self.flat = flat if flat is not None else torch.zeros(self.numel, dtype=dtype, device=device)
+        self.arena_off = arena_off                                        # (padding stays zero: a SUM all-reduce keeps it zero)
         self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
         self.pending = len(params)
         self.launched = False
@@ -93,13 +99,67 @@ class GradReducer:
             groups.append(cur)
         if tail_start < len(ready_order):
             groups.append(list(ready_order[tail_start:]))
-        buckets = [_Bucket([self._named[n] for n in g], g, self.device, torch.float32) for g in groups]
+        plists = [[self._named[n] for n in g] for g in groups]
+        arena = self._symmetric_arena(sum(_Bucket.padded_numel(pl) for pl in plists))
+        buckets, off = [], 0
+        for g, pl in zip(groups, plists):
+            n = _Bucket.padded_numel(pl)
+            buckets.append(_Bucket(pl, g, self.device, torch.float32, None if arena is None else arena[off:off + n], off))
+            off += n
         self.buckets = buckets
         self._slot = {}
         for bi, b in enumerate(buckets):
             for pi, p in enumerate(b.params):
                 self._slot[id(p)] = (bi, pi)
         self._register_sinks()
+
+    # ------------------------------------------------------------------ symmetric memory (NVLink / NVSwitch all-reduce)
+    def _symmetric_arena(self, numel):
+        """One symmetric allocation for ALL buckets (+ the flag block of csrc/allreduce.cu): every rank's copy is mapped into
+        every process, and behind one multicast address where the fabric supports it.  Returns the local fp32 tensor (the
+        buckets are slices of it) or None -> ordinary tensors + NCCL (CPU / gloo, world 1, OCT_ALLREDUCE=nccl, or a platform
+        where the rendezvous fails — reported once on rank 0, never silent)."""
+        import os
+        self._sym = None
+        if self.device.type != "cuda" or self.world == 1 or os.environ.get("OCT_ALLREDUCE", "sym") == "nccl":
+            return None
+        try:
+            import ctypes
+            import torch.distributed._symmetric_memory as symm
+            from . import _lib
+            lib = _lib.load()
+            flag_elems = lib.oct_allreduce_flag_bytes() // 4
+            total = numel + flag_elems
+            arena = symm.empty(total, dtype=torch.float32, device=self.device)
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            hdl = symm.rendezvous(arena, group)
+            arena.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.pg)                                  # flags are zero everywhere before anybody signals
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            mc = 0 if os.environ.get("OCT_ALLREDUCE", "sym") == "peer" else int(getattr(hdl, "multicast_ptr", 0) or 0)
+            self._sym = {"arena": arena, "hdl": hdl, "mc": mc, "table": (ctypes.c_void_p * self.world)(*ptrs),
+                         "flag_off": numel * 4, "rank": dist.get_rank(self.pg),
+                         "state": torch.zeros(lib.oct_allreduce_state_bytes() // 4, dtype=torch.int32, device=self.device),
+                         "ctas": int(os.environ.get("OCT_AR_CTAS", "24"))}
+            if dist.get_rank(self.pg) == 0 and os.environ.get("OCT_VERBOSE"):
+                print(f"[octcubem_b200] gradient all-reduce: symmetric memory, {'multicast (NVLS)' if mc else 'peer loads/stores'}, "
+                      f"{total * 4 / 2**20:.0f} MiB per rank", flush=True)
+            return arena[:numel]
+        except Exception as e:  # noqa: BLE001
+            if dist.get_rank(self.pg) == 0:
+                print(f"[octcubem_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+            self._sym = None
+            return None
+
+    def allreduce_backend(self) -> str:
+        if getattr(self, "_sym", None) is None:
+            return "nccl" if self.world > 1 else "none"
+        return "symmetric-multicast" if self._sym["mc"] else "symmetric-peer"
+
+    def peer_timeout(self) -> bool:
+        """True if an all-reduce kernel ever gave up waiting for a peer (synchronises; diagnostics)."""
+        return getattr(self, "_sym", None) is not None and bool(int(self._sym["state"].view(-1, 4)[:, 2].sum()) != 0)
 
     def _register_sinks(self):
         """CUDA path: the autograd Functions in ops.py write weight / bias gradients directly into the bucket views."""
@@ -157,9 +217,19 @@ class GradReducer:
             if ops._wgrad_pending.get(self.device.index, False):  # weight gradients are produced on their own stream
                 self.stream.wait_stream(ops.wgrad_stream(self.device))
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg)
-                if not self._prescaled:
-                    b.flat.mul_(1.0 / self.world)
+                sym = getattr(self, "_sym", None)
+                if sym is not None:
+                    import ctypes
+                    from . import _lib
+                    rc = _lib.load().oct_allreduce_sym(
+                        ctypes.c_void_p(sym["mc"]) if sym["mc"] else None, sym["table"], sym["flag_off"],
+                        ctypes.c_void_p(sym["state"].data_ptr()), b.arena_off, b.numel, sym["rank"], self.world, 0,
+                        1.0 if self._prescaled else 1.0 / self.world, sym["ctas"], ctypes.c_void_p(self.stream.cuda_stream))
+                    _lib.check(rc, "oct_allreduce_sym")
+                else:
+                    dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg)
+                    if not self._prescaled:
+                        b.flat.mul_(1.0 / self.world)
         else:
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
@@ -253,6 +323,7 @@ class GradReducer:
         self._clear_sinks()
         self.buckets, self._slot, self._order, self._discovering = None, {}, [], True
         self._seen = set()
+        self._sym = None
 
     def remove(self):
         self._clear_sinks()

@@ -353,7 +353,7 @@ class MaskedAutoencoderViT(nn.Module):
             assert pos_tmp.shape[0] == Tp, "temporal pos-embed length != T' (models...:429-436 would fail to broadcast)"
         cls_row = (self.cls_token + self.pos_embed_class).reshape(-1)
         x = ops.EmbedTokensFn.apply(x.contiguous().float(), pe.proj.weight, pe.proj.bias, ids_keep, pos_sp, pos_tmp, cls_row,
-                                    pe.patch_size[0], pe.t_patch_size, rt.act_dtype)
+                                    pe.patch_size[0], pe.t_patch_size, rt.act_dtype, rt.lp(pe.proj.weight))
         residual = None
         for blk in self.blocks:
             x, residual = blk(x, residual)
@@ -424,9 +424,10 @@ class MaskedAutoencoderViT(nn.Module):
         replaces the torch.rand draw of models...:350 for reproducible masks."""
         self._rt.shadows.begin_step()
         high_res = self._is_high_res(imgs.shape[-2])
-        latent, mask, ids_restore = self.forward_encoder(imgs, mask_ratio, noise=noise)
-        pred_full = self._decoder_tokens(latent, ids_restore, high_res)
-        loss = self._loss(imgs, pred_full, 1, mask, frame_loss)
+        with ops.forward_pdl():
+            latent, mask, ids_restore = self.forward_encoder(imgs, mask_ratio, noise=noise)
+            pred_full = self._decoder_tokens(latent, ids_restore, high_res)
+            loss = self._loss(imgs, pred_full, 1, mask, frame_loss)
         return loss, pred_full[:, 1:, :], mask
 
     # ------------------------------------------------------------------ optimizer hand-shake (optim.FusedAdamW)

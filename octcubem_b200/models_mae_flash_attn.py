@@ -199,7 +199,7 @@ class MaskedAutoencoderViT(nn.Module):
         cls_row = (self.cls_token + self.pos_embed[:, :1, :]).reshape(-1)
         # (x + pos)[ids_keep] == x[ids_keep] + pos[ids_keep]: the fused front end adds the table after the gather
         x = ops.EmbedTokensFn.apply(x.contiguous().float().view(N, 1, C, H, W), pe.proj.weight, pe.proj.bias, ids_keep,
-                                    pos[1:].contiguous(), None, cls_row, pe.patch_size[0], C, rt.act_dtype)
+                                    pos[1:].contiguous(), None, cls_row, pe.patch_size[0], C, rt.act_dtype, rt.lp(pe.proj.weight))
         residual = None
         for blk in self.blocks:
             x, residual = blk(x, residual)

@@ -110,7 +110,7 @@ class VisionTransformer(nn.Module):
             cls_row = (self.cls_token[0, 0] + table[0]) if self.cls_embed else None
         ids_all = torch.arange(L, device=x.device, dtype=torch.int64).expand(N, L).contiguous()  # nothing is masked
         x = ops.EmbedTokensFn.apply(x.contiguous().float(), pe.proj.weight, pe.proj.bias, ids_all, pos_sp.contiguous(), pos_tmp,
-                                    cls_row, pe.patch_size[0], pe.t_patch_size, rt.act_dtype)
+                                    cls_row, pe.patch_size[0], pe.t_patch_size, rt.act_dtype, rt.lp(pe.proj.weight))
         hidden, residual = [], None
         for blk in self.blocks:
             x, residual = blk(x, residual)

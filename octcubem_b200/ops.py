@@ -7,8 +7,11 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
+
+_os_environ_get = os.environ.get
 
 from . import _lib
 from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE, GEMM_NN, GEMM_NT, GEMM_TN, OCT_BF16, OCT_F32,
@@ -52,6 +55,23 @@ def _call(name, *args):
 
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+class forward_pdl:
+    """Programmatic dependent launch for the kernels of a FORWARD pass (oct_set_pdl): inside the context the hot
+    kernels' prologues overlap the tail of their predecessors.  Off in the backward pass, where early-resident CTAs of the dgrad
+    chain would take the SMs the side-stream weight-gradient GEMMs fill.  OCT_PDL_FWD=0 disables it."""
+    enabled = _os_environ_get("OCT_PDL_FWD", "1") != "0"
+
+    def __enter__(self):
+        if forward_pdl.enabled:
+            _lib.load().oct_set_pdl(1)
+        return self
+
+    def __exit__(self, *exc):
+        if forward_pdl.enabled:
+            _lib.load().oct_set_pdl(-1)
+        return False
 
 
 def compute_of(dtype):
@@ -156,6 +176,7 @@ _sinks_cb_queued = [False]
 
 def _sinks_pass_done():
     _sinks_written.clear()
+    _ln_seen.clear()
     _sinks_cb_queued[0] = False
 
 
@@ -174,10 +195,15 @@ def _sink(ptr, shape):
     g = param.grad
     live = ptr in _sinks_written or (g is not None and g.data_ptr() == view.data_ptr())
     _sinks_written.add(ptr)
+    _ensure_pass_callback()
+    return view.view(shape), (1 if live else 0), not live
+
+
+def _ensure_pass_callback():
+    """Per-pass bookkeeping (_sinks_written, _ln_seen) is cleared by an autograd-engine callback at the end of the pass."""
     if not _sinks_cb_queued[0]:
         _sinks_cb_queued[0] = True
         torch.autograd.Variable._execution_engine.queue_callback(_sinks_pass_done)
-    return view.view(shape), (1 if live else 0), not live
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -277,19 +303,65 @@ def add_ln_fwd(h, res_in, gamma, beta, eps, y_dtype, want_res_out):
     return y, res_out, mean, rstd
 
 
-def add_ln_bwd(dy, x, mean, rstd, gamma, dres_in, want_f32, want_lp):
+def add_ln_bwd(dy, x, mean, rstd, gamma, dres_in, want_f32, want_lp, beta_param=None):
+    """-> (dx_f32, dx_lp, dgamma, dbeta).  `beta_param` (the LayerNorm bias Parameter, optional) enables the deferred reduction:
+    dx continues the dgrad chain while the fixed-order reduction of the dgamma / dbeta partials — a leaf, like the weight
+    gradients — runs on their side stream, straight into the reducer's bucket views when those are registered (66 launches per
+    step off the critical path).  dgamma / dbeta come back as None when they were accumulated into live gradients in place."""
     _chk(dy, x, mean, rstd, gamma, dres_in)
     C = x.shape[-1]
     M = x.numel() // C
     dx_f32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
     dx_lp = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_lp else None
-    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
     nb = _lib.load().oct_add_ln_bwd_ws_bytes(M, C)
     ws = _ws(nb, x.device)
-    _call("oct_add_ln_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres_in), _p(dx_f32), _p(dx_lp),
-          OCT_BF16, _p(dgamma), _p(dbeta), _p(ws), ws.numel(), M, C, _stream())
+    dev = x.device
+    defer = overlap_wgrad and beta_param is not None and dy.dtype == torch.bfloat16
+    if defer:
+        # only when nobody on the CURRENT stream reads the results before the end-of-pass join: the first gradient of each
+        # parameter in this pass, with no live .grad (autograd then adopts the tensors without touching them)
+        keys = (gamma.data_ptr(), beta_param.data_ptr())
+        g_dst, g_beta, g_give = _sink(keys[0], (C,))
+        b_dst, b_beta, b_give = _sink(keys[1], (C,))
+        fresh = all(k not in _ln_seen for k in keys) and g_beta == 0 and b_beta == 0
+        if g_dst is None:   # no reducer: plain autograd gradients
+            fresh = fresh and _param_grad_is_none(gamma) and _param_grad_is_none(beta_param)
+        _ln_seen.update(keys)
+        _ensure_pass_callback()
+        if not fresh:
+            defer = False
+            if _wgrad_pending.get(dev.index, False):  # order behind earlier deferred writes into the same buffers
+                torch.cuda.current_stream(dev).wait_stream(wgrad_stream(dev))
+    if not defer:
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        _call("oct_add_ln_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres_in), _p(dx_f32), _p(dx_lp),
+              OCT_BF16, _p(dgamma), _p(dbeta), _p(ws), ws.numel(), M, C, _stream())
+        return dx_f32, dx_lp, dgamma, dbeta
+    dgamma = g_dst if g_dst is not None else torch.empty(C, dtype=torch.float32, device=dev)
+    dbeta = b_dst if b_dst is not None else torch.empty(C, dtype=torch.float32, device=dev)
+    nblocks = ctypes.c_int(0)
+    _call("oct_add_ln_bwd_main", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres_in), _p(dx_f32), _p(dx_lp),
+          OCT_BF16, _p(ws), ws.numel(), M, C, ctypes.byref(nblocks), _stream())
+    side, cur = wgrad_stream(dev), torch.cuda.current_stream(dev)
+    _wgrad_pending[dev.index] = True
+    torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad(dev))
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        _call("oct_add_ln_bwd_finish", _p(ws), nblocks.value, C, _p(dgamma), _p(dbeta), _stream())
+    for t in (ws, dgamma, dbeta):
+        t.record_stream(side)
     return dx_f32, dx_lp, dgamma, dbeta
+
+
+_ln_seen = set()      # LayerNorm parameters that already received a gradient in the running backward pass
+_param_by_ptr = {}    # storage pointer -> LayerNorm Parameter (registered by AddLNFn.forward; weak by construction: ptr reuse is harmless,
+                      # a stale entry can only make a step take the synchronous path)
+
+
+def _param_grad_is_none(t):
+    p = _param_by_ptr.get(t.data_ptr())
+    return p is not None and p.grad is None
 
 
 def attn_fwd(qkv, H, d, compute):
@@ -453,6 +525,12 @@ class AddLNFn(torch.autograd.Function):
             raise RuntimeError("AddLNFn: res_in given but residual not kept")
         y, res_out, mean, rstd = add_ln_fwd(h, res_in, gamma, beta, eps, y_dtype, keep_residual)
         x = res_out if keep_residual else h  # the tensor that was normalised
+        if isinstance(gamma, torch.nn.Parameter) and isinstance(beta, torch.nn.Parameter):
+            _param_by_ptr[gamma.data_ptr()] = gamma
+            _param_by_ptr[beta.data_ptr()] = beta
+            ctx.beta_param = beta
+        else:
+            ctx.beta_param = None
         ctx.save_for_backward(x, mean, rstd, gamma)
         ctx.h_dtype = h.dtype
         ctx.has_res_in = res_in is not None
@@ -467,7 +545,7 @@ class AddLNFn(torch.autograd.Function):
             dres = dres.contiguous()
         h_lp = ctx.h_dtype == torch.bfloat16
         want_f32 = ctx.has_res_in or not h_lp
-        dx_f32, dx_lp, dgamma, dbeta = add_ln_bwd(dy, x, mean, rstd, gamma, dres, want_f32, h_lp)
+        dx_f32, dx_lp, dgamma, dbeta = add_ln_bwd(dy, x, mean, rstd, gamma, dres, want_f32, h_lp, ctx.beta_param)
         dh = dx_lp if h_lp else dx_f32
         dres_in = dx_f32 if ctx.has_res_in else None
         return dh, dres_in, dgamma, dbeta, None, None, None
@@ -513,36 +591,34 @@ class GatherTokensFn(torch.autograd.Function):
 
 class EmbedTokensFn(torch.autograd.Function):
     """Fused encoder front end: PatchEmbed (vv:74-83) -> random_masking gather (models:362-363) -> cls + pos add
-    (models:409-478).  Forward runs the dense im2col-free tcgen05 patch-embed (bf16 mode) or patchify + fp32 GEMM
-    (fp32 mode).  Backward touches only the kept tokens: dW = dX_keep^T · patches_keep, db = colsum(dX_keep)."""
+    (models:409-478), GATHER FIRST: `ids_keep` depends only on the noise, so only the kept tokens (10 % at mask 0.9) are
+    patchified and embedded — one [B*keep, u*p*p] x [E, u*p*p]^T GEMM with the bias in its epilogue (bf16 operands, which is
+    also what the reference's Conv3d computes under autocast; fp32 in the parity mode) instead of the dense embedding of all L
+    tokens followed by a gather.  The kept patches are saved: the backward's dW = dX_keep^T · patches_keep needs them again.
+    `w_lp`: bf16 shadow of the Conv3d weight (None in fp32 mode)."""
 
     @staticmethod
-    def forward(ctx, imgs, weight, bias, ids_keep, pos_sp, pos_tmp, cls_row, p, u, act_dtype):
-        _chk(imgs, weight, bias, ids_keep, pos_sp, pos_tmp, cls_row)
+    def forward(ctx, imgs, weight, bias, ids_keep, pos_sp, pos_tmp, cls_row, p, u, act_dtype, w_lp=None):
+        _chk(imgs, weight, bias, ids_keep, pos_sp, pos_tmp, cls_row, w_lp)
         B, _, T, H, W = imgs.shape
         E = weight.shape[0]
-        w2d = weight.view(E, -1)
-        if act_dtype == torch.bfloat16:
-            x = patch_embed_tc(imgs, w2d, bias, p, u, torch.bfloat16)
-        else:
-            patches = patchify(imgs, p, u, torch.float32)
-            L = patches.shape[1]
-            x = gemm(GEMM_NT, patches.view(B * L, -1), w2d, B * L, E, w2d.shape[1], torch.float32, EPI_BIAS, bias=bias)
-            x = x.view(B, L, E)
-        L = x.shape[1]
+        w2d = (weight if w_lp is None else w_lp).view(E, -1)
+        L = (T // u) * (H // p) * (W // p)
         keep = ids_keep.shape[1]
         G = pos_sp.shape[0]
+        pk = patchify(imgs, p, u, act_dtype, ids_keep=ids_keep).view(B * keep, -1)
+        x = gemm(GEMM_NT, pk, w2d, B * keep, E, w2d.shape[1], act_dtype, EPI_BIAS, bias=bias)
         out = torch.empty(B, keep + (1 if cls_row is not None else 0), E, dtype=torch.float32, device=imgs.device)
-        _call("oct_gather_tokens_fwd", _p(x), _dt(x), _p(ids_keep), _p(pos_sp), _p(pos_tmp), _p(cls_row), _p(out), B, L, keep,
+        _call("oct_posadd_tokens_fwd", _p(x), _dt(x), _p(ids_keep), _p(pos_sp), _p(pos_tmp), _p(cls_row), _p(out), B, L, keep,
               G, E, _stream())
-        ctx.save_for_backward(imgs, ids_keep)
-        ctx.dims = (B, L, keep, G, E, p, u, act_dtype, pos_tmp is not None, cls_row is not None, tuple(weight.shape))
+        ctx.save_for_backward(pk, ids_keep)
+        ctx.dims = (B, L, keep, G, E, act_dtype, pos_tmp is not None, cls_row is not None, tuple(weight.shape))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        imgs, ids_keep = ctx.saved_tensors
-        B, L, keep, G, E, p, u, act_dtype, has_tmp, has_cls, wshape = ctx.dims
+        pk, ids_keep = ctx.saved_tensors
+        B, L, keep, G, E, act_dtype, has_tmp, has_cls, wshape = ctx.dims
         if not dout.is_contiguous():
             dout = dout.contiguous()
         dev = dout.device
@@ -552,9 +628,8 @@ class EmbedTokensFn(torch.autograd.Function):
         d_cls = torch.empty(E, dtype=torch.float32, device=dev) if has_cls else None
         _call("oct_gather_tokens_bwd", _p(dout), _p(ids_keep), _p(dxk), _dt(dxk), _p(d_sp), _p(d_tmp), _p(d_cls), B, L, keep, G,
               E, _stream())
-        pk = patchify(imgs, p, u, act_dtype, ids_keep=ids_keep).view(B * keep, -1)
         dw, db = wgrad_bias(dxk, pk)
-        return None, dw.view(wshape), db, None, d_sp, d_tmp, d_cls, None, None, None
+        return None, dw.view(wshape), db, None, d_sp, d_tmp, d_cls, None, None, None, None
 
 
 class UnshuffleFn(torch.autograd.Function):

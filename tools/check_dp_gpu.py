@@ -1,4 +1,4 @@
-"""torchrun check of dp.GradReducer on GPUs (NCCL): the reduced gradients of a toy 3D-MAE step on `world` ranks must equal
+"""torchrun check of dp.GradReducer on GPUs (symmetric-memory all-reduce of csrc/allreduce.cu, or NCCL with OCT_ALLREDUCE=nccl): the reduced gradients of a toy 3D-MAE step on `world` ranks must equal
 the mean of the per-rank gradients computed locally without the reducer (DDP semantics), with the wgrad GEMMs writing
 straight into the all-reduce buckets and the backward seeded with 1/world.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/check_dp_gpu.py
@@ -54,6 +54,36 @@ for step in range(3):  # step 0 = discovery (non-overlapped), then the hooked / 
         assert err < 2e-3, (step, k, err)  # same bf16 kernels on both sides; only the split-K / reduction order differs
 in_place = sum(1 for k, p in model.named_parameters() if p.grad is not None and p.data_ptr() in ops.grad_sinks
                and p.grad.data_ptr() == ops.grad_sinks[p.data_ptr()][0].data_ptr())
-print(f"rank {rank}: OK, worst rel err {worst:.2e}, {in_place} gradients live in their buckets, {len(red.buckets)} buckets", flush=True)
+# a second pass through a CUDA graph (device-resident epochs of the symmetric all-reduce must survive replay)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+
+
+def one():
+    red.zero_grad()
+    loss, _, _ = model(vols[rank], mask_ratio=0.75, noise=noises[rank])
+    red.backward(loss)
+    red.finish()
+
+
+with torch.cuda.stream(side):
+    one()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    one()
+for _ in range(3):
+    graph.replay()
+torch.cuda.synchronize()
+for k, p in model.named_parameters():
+    if p.grad is not None:
+        err = float((p.grad - ref[k]).norm() / (ref[k].norm() + 1e-20))
+        worst = max(worst, err)
+        assert err < 2e-3, ("graph", k, err)
+assert not red.peer_timeout(), "an all-reduce kernel timed out waiting for a peer"
+print(f"rank {rank}: OK, worst rel err {worst:.2e}, {in_place} gradients live in their buckets, {len(red.buckets)} buckets, "
+      f"all-reduce backend: {red.allreduce_backend()}", flush=True)
+del graph
 dist.barrier()
 dist.destroy_process_group()
