@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int kArMaxWorld = 16;
-constexpr int kArThreads = 512;
+constexpr int kArThreads = 128;   // 128 threads x <= 48 registers: the CTA fits NEXT TO a 320-thread x 165-register GEMM CTA on the same SM
 
 struct ArPeers {
   float* buf[kArMaxWorld];        // rank s's buffer (peer path: data; both paths: flag block at flag_off)
@@ -156,10 +156,10 @@ extern "C" int oct_allreduce_sym(void* mc_ptr, const void* const* peer_bufs, int
     OCT_REQUIRE(s >= world || (peers.buf[s] && aligned16(peers.buf[s])), "oct_allreduce_sym: peer buffer %d null or unaligned", s);
   }
   if (n_elems == 0) return OCT_OK;
-  if (ctas <= 0) ctas = 24;
+  if (ctas <= 0) ctas = 96;
   const int64_t need = ceil_div64(ceil_div64(n_elems / 4, world), kArThreads);
   if (ctas > need) ctas = (int)(need < 1 ? 1 : need);
-  if (ctas > 64) ctas = 64;   // every CTA must become resident while the others spin on the flags
+  if (ctas > 296) ctas = 296;   // every CTA must become resident while the others spin on the flags
   cudaStream_t st = (cudaStream_t)stream;
   if (mc_ptr)
     allreduce_kernel<true><<<ctas, kArThreads, 0, st>>>((float*)mc_ptr, peers, (size_t)flag_off_bytes / 4, (unsigned*)state,

@@ -31,7 +31,7 @@
 
 namespace {
 
-constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 512, AB_SM_THREADS = 256, AB_DRAIN_THREADS = 128, AB_Q_STAGES = 2;
+constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 512, AB_SM_THREADS = 256, AB_DRAIN_THREADS = 128;
 // register budget (setmaxnreg, per warpgroup): 8 softmax warps x 176 + 8 control / drain warps x 80 = 64 K registers
 constexpr int AB_REGS_SOFTMAX = 176, AB_REGS_OTHER = 80;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -45,7 +45,11 @@ struct AbCfg {
   static constexpr int kDsBytes = 2 * 128 * 128;  // one dS^T staging tile: two 64-query chunks of [128 kv rows x 128 B]
   static constexpr int kDqBytes = 128 * HD * 4;   // fp32 dQ tile staged for the bulk reduce (16-byte chunks XOR-swizzled)
   // smem: K, V | Q[2], dO[2] | dS[2] | dQ staging | lse2[2][128], delta[2][128] | barriers
-  static constexpr int kSmem = 2 * kTileBytes + 2 * AB_Q_STAGES * kTileBytes + 2 * kDsBytes + kDqBytes + 8 * 2 * 64 * 4 + 1024 + 256;
+  // Q / dO ring depth.  The stage of query tile m + kQStages is refilled once tile m has been consumed; with two stages that
+  // is ONE sub-tile (~1400 clk) before the issuer needs the data, less than a TMA round trip: the clock64 trace showed the
+  // issuer waiting ~1100 clk for q_full at every second sub-tile (38 % of the kernel).  head_dim 64 has no room for more.
+  static constexpr int kQStages = (HD == 32) ? 4 : 2;
+  static constexpr int kSmem = 2 * kTileBytes + 2 * kQStages * kTileBytes + 2 * kDsBytes + kDqBytes + 8 * 2 * 64 * 4 + 1024 + 256;
   // TMEM columns: stage s of the fp32 sub-tiles: S^T at 128 s, dP^T at 128 s + 64; accumulators behind them
   static constexpr uint32_t kColST = 0, kColDPT = 64, kStageCols = 128;
   static constexpr uint32_t kColDV = 256, kColDK = 256 + HD, kColDQ = 256 + 2 * HD;
@@ -99,16 +103,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = sK + C::kTileBytes;
-  uint8_t* sQ = sV + C::kTileBytes;                       // [AB_Q_STAGES]
-  uint8_t* sDO = sQ + AB_Q_STAGES * C::kTileBytes;        // [AB_Q_STAGES]
-  uint8_t* sDS = sDO + AB_Q_STAGES * C::kTileBytes;       // [2] x 32 KB, 1024-aligned (all tiles are multiples of 8 KB)
+  uint8_t* sQ = sV + C::kTileBytes;                       // [C::kQStages]
+  uint8_t* sDO = sQ + C::kQStages * C::kTileBytes;        // [C::kQStages]
+  uint8_t* sDS = sDO + C::kQStages * C::kTileBytes;       // [2] x 32 KB, 1024-aligned (all tiles are multiples of 8 KB)
   uint8_t* sDQ = sDS + 2 * C::kDsBytes;                   // [128][HD] fp32, swizzled
   float* sStat = reinterpret_cast<float*>(sDQ + C::kDqBytes);  // [8 warps][2 slots][32 x -lse*log2e | 32 x -delta]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 8 * 2 * 64);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;                 // [2]
-  uint64_t* q_empty = q_full + AB_Q_STAGES;    // [2]
-  uint64_t* sdp_full = q_empty + AB_Q_STAGES;  // [2] per fp32 stage, one completion every other sub-tile
+  uint64_t* q_empty = q_full + C::kQStages;    // [2]
+  uint64_t* sdp_full = q_empty + C::kQStages;  // [2] per fp32 stage, one completion every other sub-tile
   uint64_t* p_ready = sdp_full + 2;            // [2] per fp32 stage (256 arrivals)
   uint64_t* dq_full = p_ready + 2;             // once per query tile
   uint64_t* dq_free = dq_full + 1;             // once per query tile (the 128 drain threads)
@@ -127,7 +131,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     tc::prefetch_tmap(&tmap_qkv);
     tc::prefetch_tmap(&tmap_do);
     tc::mbar_init(kv_full, 1);
-    for (int s = 0; s < AB_Q_STAGES; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
+    for (int s = 0; s < C::kQStages; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&sdp_full[s], 1); tc::mbar_init(&p_ready[s], AB_SM_THREADS); }
     tc::mbar_init(dq_full, 1);
     tc::mbar_init(dq_free, AB_DRAIN_THREADS);
@@ -162,7 +166,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         tc::mbar_arrive_expect_tx(&q_full[stage], 2 * C::kTileBytes);
         tc::tma_load_4d(sQ + stage * C::kTileBytes, &tmap_qkv, &q_full[stage], 0, h, m * AB_T, b);
         tc::tma_load_4d(sDO + stage * C::kTileBytes, &tmap_do, &q_full[stage], 0, h, m * AB_T, b);
-        if (++stage == AB_Q_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == C::kQStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 9) {
@@ -186,15 +190,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       constexpr uint32_t kStageStep = C::kTileBytes >> 4, kHalfStep = (AB_SUB * C::kRowBytes) >> 4;
       constexpr uint32_t kKStepK = 32 >> 4, kKStepMN = (16 * C::kRowBytes) >> 4, kKStepDS = (16 * 128) >> 4;
       constexpr uint32_t kDsBufStep = C::kDsBytes >> 4;
-      // sub-tile j -> (q tile j>>1, half j&1); its Q/dO ring stage is (j>>1) % AB_Q_STAGES, its fp32 stage is j&1
+      // sub-tile j -> (q tile j>>1, half j&1); its Q/dO ring stage is (j>>1) % C::kQStages, its fp32 stage is j&1
       auto wait_q = [&](int j) {  // all lanes: first use of Q/dO tile j >> 1
         if ((j & 1) == 0) {
-          tc::mbar_wait(&q_full[(j >> 1) % AB_Q_STAGES], ((j >> 1) / AB_Q_STAGES) & 1);
+          tc::mbar_wait(&q_full[(j >> 1) % C::kQStages], ((j >> 1) / C::kQStages) & 1);
           tc::tcgen05_fence_after();
         }
       };
       auto issue_sdp = [&](int j) {  // elected lane: S^T = K Q_h^T ; dP^T = V dO_h^T into fp32 stage j&1
-        const int qstage = (j >> 1) % AB_Q_STAGES;
+        const int qstage = (j >> 1) % C::kQStages;
         const uint32_t off = qstage * kStageStep + (j & 1) * kHalfStep;
         const uint32_t tcol = tmem_base + (j & 1) * C::kStageCols;
 #pragma unroll
@@ -214,7 +218,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       __syncwarp();
       for (int i = 0; i < n_sub; ++i) {
         const int m = i >> 1, hh = i & 1, st = i & 1;
-        const int qstage = m % AB_Q_STAGES;
+        const int qstage = m % C::kQStages;
         const uint32_t off = qstage * kStageStep + hh * kHalfStep;
         const uint32_t tcol = tmem_base + st * C::kStageCols;
         AB_TRACE(0);
@@ -224,7 +228,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         // which only the drain warps need.
         const bool dq_now = (hh == 1) || (i == n_sub - 1);
         AB_WAIT(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
+        AB_TRACE(10);
         if (i + 2 < n_sub) wait_q(i + 2);
+        AB_TRACE(11);
         if (dq_now && m > 0) tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM (long ago)
         tc::tcgen05_fence_after();
         AB_TRACE(1);

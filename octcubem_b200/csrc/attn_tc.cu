@@ -11,17 +11,11 @@
 //              pipe executes in issue order), so a warpgroup's next score tile is complete before it finishes the
 //              current one — with one buffer per Q tile the PV -> QK -> commit turnaround (~500 clk) sat on every
 //              warpgroup's critical path and the SFU idled 40 % of the time (profiles/r1_attention_ncu.md).
-//   warps 2-9  softmax warps of Q tile 0, warps 10-17 of Q tile 1: TWO warps per TMEM lane quarter (lane = query row), each
-//              owning 64 of the tile's 128 score columns.  Online softmax in the log2 domain with lazy rescaling (O is only
-//              rescaled when the running max grows by more than 2^8), P written back over S as bf16.  The two warps of a row
-//              exchange their partial row maxima through shared memory (one 64-thread named barrier per tile, which also
-//              orders "both halves of S are in registers" before either half of P overwrites them); the partial row sums
-//              meet only in the epilogue.
-// The kernel is bound by the exponentials for head_dim 32 (128 MMA flops per score element) — in practice by
-// the LATENCY around them: with one warp per row (round 1: 8 softmax warps, 168 registers, two warps per scheduler) the
-// issue slots were 52 % used and the XU pipe 59 % (profiles/r1_attention_ncu.md; TMEM loads are not the limit: 110 B/clk
-// per warp, 700 B/clk per SM, tools/microbench/tmem.cu).  Four warps per scheduler with half the registers each hide it.
-// head_dim 64 uses 128B swizzle, head_dim 32 uses 64B swizzle (TMA row pitch = inner box extent).
+//   warps 2-5  softmax warpgroup of Q tile 0, warps 6-9 of Q tile 1: thread <-> query row (TMEM lane), online softmax in
+//              the log2 domain with lazy rescaling (O is only rescaled when the running max grows by more than 2^8),
+//              P written back over S as bf16.
+// The kernel is MUFU(ex2)-bound for head_dim 32 (128 MMA flops per score element): two warps per scheduler
+// keep the SFU pipe busy.  head_dim 64 uses 128B swizzle, head_dim 32 uses 64B swizzle (TMA row pitch = inner box extent).
 #include "tc_common.cuh"
 
 #ifndef OCT_AT_POLY_EVERY  // one exponential pair in OCT_AT_POLY_EVERY is evaluated on the FMA pipe (0 = none)
@@ -38,7 +32,7 @@
 
 namespace {
 
-constexpr int AT_BM = 128, AT_BN = 128, AT_QT = 2, AT_THREADS = 64 + AT_QT * 256, AT_KV_STAGES = 4, AT_SBUFS = 3;
+constexpr int AT_BM = 128, AT_BN = 128, AT_QT = 2, AT_THREADS = 64 + AT_QT * 128, AT_KV_STAGES = 4, AT_SBUFS = 3;
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -48,8 +42,7 @@ struct AtCfg {
   static constexpr int kTileBytes = 128 * kRowBytes;             // one 128-row Q / K / V tile
   static constexpr uint32_t kSwz = (HD == 64) ? tc::kSwz128 : tc::kSwz64;
   static constexpr uint32_t kSBO = 8 * kRowBytes;                // 8-row swizzle atom
-  static constexpr int kXchgBytes = AT_QT * 2 * 2 * 128 * 4;     // partial row maxima [tile][parity][half][row]
-  static constexpr int kSmem = kTileBytes * (AT_QT + 2 * AT_KV_STAGES) + kXchgBytes + 1024 + 256;
+  static constexpr int kSmem = kTileBytes * (AT_QT + 2 * AT_KV_STAGES) + 1024 + 256;
   static constexpr uint32_t kColS = 0;                  // score tile n = 2j + t at kColS + 128 (n % AT_SBUFS)
   static constexpr uint32_t kColO = 128 * AT_SBUFS;     // O_t at kColO + HD t  (384 + 2 HD <= 512)
 };
@@ -67,43 +60,39 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
-// One 128x128 score tile, one query row, the 64 columns [64 half, 64 half + 64) of it: online-softmax update (m in the log2
-// domain, l = this warp's partial row sum), P written over S as bf16.  kMasked = last kv tile (columns >= valid do not exist);
-// the common full tile carries no per-element predicates.  `xm` = this row's two exchange slots of the tile's parity.
+// One 128x128 score tile of one query row: online-softmax update (m, l in the log2 domain), P written over S as bf16.
+// kMasked = last kv tile (columns >= valid do not exist); the common full tile carries no per-element predicates.
 template <int HD, bool kMasked>
-__device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, uint64_t* o_done, int j, int valid, int half,
-                                             float* xm, int bar_id, float scale_log2e, float& m, float& l) {
-  // Single pass over TMEM: this warp's 64 score columns are held in registers.
-  uint32_t sr[2][32];
+__device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, uint64_t* o_done, int j, int valid,
+                                             float scale_log2e, float& m, float& l) {
+  // Single pass over TMEM: the whole 128-column score row is held in registers (tcgen05.ld runs at ~64 B/clk/SM, so
+  // reading S twice — once for the maximum, once for the exponentials — made the kernel TMEM-load-bound).
+  uint32_t sr[4][32];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) tc::tmem_ld_x32(tmem_s + half * 64 + c * 32, sr[c]);
+  for (int c = 0; c < 4; ++c) tc::tmem_ld_x32(tmem_s + c * 32, sr[c]);
   tc::tmem_ld_wait();
   if (kMasked) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (half * 64 + c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf
+        if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf
   }
-  // eight independent 3-input max chains (4 deep): the row maximum sits on the critical path of every tile
+  // eight independent 3-input max chains (8 deep) instead of two (32 deep): the row maximum sits on the critical path of
+  // every tile (nothing else of this warp can issue until it is known), so its latency, not its instruction count, matters
   float mx[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int i = 0; i < 32; i += 16) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         mx[q] = max3(mx[q], __uint_as_float(sr[c][i + 2 * q]), __uint_as_float(sr[c][i + 2 * q + 1]));
     }
-  const float m_half = fmaxf(max3(mx[0], mx[1], mx[2]), fmaxf(max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-  // exchange with the warp that owns the other 64 columns of this row.  The barrier also guarantees that BOTH warps hold
-  // their scores in registers before either writes P: bf16 P of columns [64, 128) lands on the fp32 S columns [32, 64).
-  xm[half * 128] = m_half;
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-  const float m_tile = fmaxf(m_half, xm[(half ^ 1) * 128]) * scale_log2e;
-  const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf); identical in both warps
+  const float m_tile = fmaxf(max3(mx[0], mx[1], mx[2]), fmaxf(max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * scale_log2e;
+  const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? m_tile : m;
     if (j > 0) {
@@ -111,13 +100,13 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
       tc::mbar_wait(o_done, (j - 1) & 1);  // O += P(j-1) V_{j-1} has landed
       tc::tcgen05_fence_after();
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {   // this warp rescales its half of the O columns
+      for (int c = 0; c < HD / 16; ++c) {
         uint32_t o[16];
-        tc::tmem_ld_x16(tmem_o + half * (HD / 2) + c * 16, o);
+        tc::tmem_ld_x16(tmem_o + c * 16, o);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-        tc::tmem_st_x16(tmem_o + half * (HD / 2) + c * 16, o);
+        tc::tmem_st_x16(tmem_o + c * 16, o);
       }
       l *= factor;
     }
@@ -125,13 +114,14 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
   }
   // P = exp2(s * c - m) as bf16 pairs written over S (masked columns hold -inf -> exactly 0).  Packed fp32x2 math
   // (FFMA2 / FADD2) halves the issue slots around the exponentials, and one pair in kPolyEvery is evaluated by
-  // exp2_poly2 on the FMA pipe (same idea as FlashAttention-4's software exp2).  The masked tile keeps the SFU for all
+  // exp2_poly2 on the FMA pipe: the loop is bound by MUFU.EX2 (16 / clk / SM), so moving a quarter of the exponentials
+  // off the SFU shortens it (same idea as FlashAttention-4's software exp2).  The masked tile keeps the SFU for all
   // columns so that -inf stays exactly 0.
   constexpr int kPolyEvery = OCT_AT_POLY_EVERY;
   const uint64_t sc2 = tc::pack2(scale_log2e, scale_log2e), nm2 = tc::pack2(-m, -m);
   uint64_t la = tc::pack2(0.f, 0.f), lb = la;
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -148,7 +138,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
       if (i & 1) lb = tc::add2(lb, tc::pack2(p0, p1)); else la = tc::add2(la, tc::pack2(p0, p1));
       pk[i] = pack_bf16x2(p0, p1);
     }
-    tc::tmem_st_x16(tmem_s + half * 32 + c * 16, pk);
+    tc::tmem_st_x16(tmem_s + c * 16, pk);
   }
   float l0, l1;
   tc::unpack2(tc::add2(la, lb), l0, l1);
@@ -156,7 +146,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
 }
 
 template <int HD>
-__global__ void __maxnreg__(112) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                     const AtParams p) {
   using C = AtCfg<HD>;
   pdl_launch_dependents();
@@ -166,8 +156,7 @@ __global__ void __maxnreg__(112) attn_fwd_tc_kernel(const __grid_constant__ CUte
   uint8_t* sQ = smem;                                   // [AT_QT]
   uint8_t* sK = smem + AT_QT * C::kTileBytes;           // [AT_KV_STAGES]
   uint8_t* sV = sK + AT_KV_STAGES * C::kTileBytes;      // [AT_KV_STAGES]
-  float* xchg = reinterpret_cast<float*>(sV + AT_KV_STAGES * C::kTileBytes);  // [AT_QT][2 parities][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + C::kXchgBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_KV_STAGES * C::kTileBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + AT_KV_STAGES;
@@ -191,7 +180,7 @@ __global__ void __maxnreg__(112) attn_fwd_tc_kernel(const __grid_constant__ CUte
     for (int s = 0; s < AT_KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
     for (int i = 0; i < AT_SBUFS; ++i) {
       tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&p_full[i], 256);
+      tc::mbar_init(&p_full[i], 128);
     }
     for (int t = 0; t < AT_QT; ++t) tc::mbar_init(&o_done[t], 1);
     tc::fence_barrier_init();
@@ -284,16 +273,13 @@ __global__ void __maxnreg__(112) attn_fwd_tc_kernel(const __grid_constant__ CUte
       }
     }
     __syncwarp();
-  } else if (((warp - 2) >> 3) <= qsh) {
-    // ===================== softmax / correction / epilogue: warps 2 + 8t .. 9 + 8t own Q tile t =====================
-    const int t = (warp - 2) >> 3;
-    const int half = ((warp - 2) >> 2) & 1;   // which 64 score columns (and which half of the O columns) of the row
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+  } else if (((warp - 2) >> 2) <= qsh) {
+    // ===================== softmax / correction / epilogue: warpgroup t owns Q tile t =====================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int bar_id = 1 + t * 4 + quarter;   // the two warps (half 0 / 1) of one (tile, lane quarter)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t tmem_o = lane_addr + C::kColO + t * HD;
-    float* xrow = xchg + t * (2 * 2 * 128) + row;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int n = (j << qsh) + t, buf = n % AT_SBUFS;
@@ -301,43 +287,38 @@ __global__ void __maxnreg__(112) attn_fwd_tc_kernel(const __grid_constant__ CUte
       tc::tcgen05_fence_after();
       const int valid = p.S - j * AT_BN;  // columns >= valid are out of range (TMA zero-filled K rows)
       const uint32_t tmem_s = lane_addr + C::kColS + buf * 128;
-      float* xm = xrow + (j & 1) * (2 * 128);
       if (valid >= AT_BN)
-        softmax_tile<HD, false>(tmem_s, tmem_o, &o_done[t], j, valid, half, xm, bar_id, p.scale_log2e, m, l);
+        softmax_tile<HD, false>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       else
-        softmax_tile<HD, true>(tmem_s, tmem_o, &o_done[t], j, valid, half, xm, bar_id, p.scale_log2e, m, l);
+        softmax_tile<HD, true>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&p_full[buf]);
     }
-    // epilogue: the two partial row sums meet, O / l -> bf16 (each warp its half of the columns), lse
-    float* xl = xrow + (n_kv & 1) * (2 * 128);   // the parity the last tile did not use
-    xl[half * 128] = l;
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    l += xl[(half ^ 1) * 128];
+    // epilogue: O / l -> bf16, lse
     tc::mbar_wait(&o_done[t], (n_kv - 1) & 1);
     tc::tcgen05_fence_after();
     const int qi = q0 + t * AT_BM + row;
     const float inv = 1.f / l;
-    __nv_bfloat16* orow = p.out + (((size_t)b * p.S + qi) * p.H + h) * HD + half * (HD / 2);
+    __nv_bfloat16* orow = p.out + (((size_t)b * p.S + qi) * p.H + h) * HD;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
-      uint32_t o[16];
-      tc::tmem_ld_x16(tmem_o + half * (HD / 2) + c * 16, o);
+      uint32_t o[32];
+      tc::tmem_ld_x32(tmem_o + c * 32, o);
       tc::tmem_ld_wait();
       if (qi < p.S) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 8) {
+        for (int i = 0; i < 32; i += 8) {
           uint4 v;
           v.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
           v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
           v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
           v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 16 + i) = v;
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) = v;
         }
       }
     }
-    if (half == 0 && qi < p.S) p.lse[((size_t)b * p.H + h) * p.S + qi] = (m + log2f(l)) * kLn2;
+    if (qi < p.S) p.lse[((size_t)b * p.H + h) * p.S + qi] = (m + log2f(l)) * kLn2;
   }
 
   tc::tcgen05_fence_before();

@@ -141,7 +141,7 @@ class GradReducer:
             self._sym = {"arena": arena, "hdl": hdl, "mc": mc, "table": (ctypes.c_void_p * self.world)(*ptrs),
                          "flag_off": numel * 4, "rank": dist.get_rank(self.pg),
                          "state": torch.zeros(lib.oct_allreduce_state_bytes() // 4, dtype=torch.int32, device=self.device),
-                         "ctas": int(os.environ.get("OCT_AR_CTAS", "24"))}
+                         "ctas": int(os.environ.get("OCT_AR_CTAS", "96"))}
             if dist.get_rank(self.pg) == 0 and os.environ.get("OCT_VERBOSE"):
                 print(f"[octcubem_b200] gradient all-reduce: symmetric memory, {'multicast (NVLS)' if mc else 'peer loads/stores'}, "
                       f"{total * 4 / 2**20:.0f} MiB per rank", flush=True)

@@ -8,7 +8,7 @@ files=${@:-"attn_tc attn_bwd_tc"}
 make -j8 >/dev/null
 mkdir -p build_$name ../variants
 objs=""
-for f in api mask ln loss gemm_simt gemm_tc attn_simt attn_tc attn_bwd_tc patch_embed_tc optim dispatch; do
+for f in api mask pool ingest ln loss gemm_simt gemm_tc attn_simt attn_tc attn_bwd_tc patch_embed_tc optim clip allreduce dispatch; do
   if [[ " $files " == *" $f "* ]]; then
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr \
       -Xptxas -v -DOCT_BUILDING $extra -c $f.cu -o build_$name/$f.o 2> build_$name/$f.ptxas.log || { cat build_$name/$f.ptxas.log; exit 1; }

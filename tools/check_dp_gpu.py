@@ -17,6 +17,10 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
+# everything below runs on ONE non-default stream: autograd pins every AccumulateGrad node to the stream of its first backward
+# pass, and a node created on the legacy default stream cannot take part in a later CUDA-graph capture
+_main_stream = torch.cuda.Stream()
+torch.cuda.set_stream(_main_stream)
 kw = dict(input_size=64, patch_size=16, in_chans=1, embed_dim=128, depth=2, num_heads=2, decoder_embed_dim=64, decoder_depth=1,
           decoder_num_heads=2, num_frames=12, t_patch_size=3, pred_t_dim=12, high_res_input_size=128, sep_pos_embed=True,
           cls_embed=True, use_flash_attn=True, precision="bf16", norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6))
@@ -55,10 +59,6 @@ for step in range(3):  # step 0 = discovery (non-overlapped), then the hooked / 
 in_place = sum(1 for k, p in model.named_parameters() if p.grad is not None and p.data_ptr() in ops.grad_sinks
                and p.grad.data_ptr() == ops.grad_sinks[p.data_ptr()][0].data_ptr())
 # a second pass through a CUDA graph (device-resident epochs of the symmetric all-reduce must survive replay)
-side = torch.cuda.Stream()
-side.wait_stream(torch.cuda.current_stream())
-
-
 def one():
     red.zero_grad()
     loss, _, _ = model(vols[rank], mask_ratio=0.75, noise=noises[rank])
@@ -66,12 +66,10 @@ def one():
     red.finish()
 
 
-with torch.cuda.stream(side):
-    one()
-torch.cuda.current_stream().wait_stream(side)
+one()
 torch.cuda.synchronize()
 graph = torch.cuda.CUDAGraph()
-with torch.cuda.graph(graph):
+with torch.cuda.graph(graph, stream=_main_stream):
     one()
 for _ in range(3):
     graph.replay()
