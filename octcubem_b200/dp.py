@@ -143,12 +143,15 @@ class GradReducer:
                          "state": torch.zeros(lib.oct_allreduce_state_bytes() // 4, dtype=torch.int32, device=self.device),
                          "ctas": int(os.environ.get("OCT_AR_CTAS", "96"))}
             if dist.get_rank(self.pg) == 0 and os.environ.get("OCT_VERBOSE"):
+                import sys
                 print(f"[octcubem_b200] gradient all-reduce: symmetric memory, {'multicast (NVLS)' if mc else 'peer loads/stores'}, "
-                      f"{total * 4 / 2**20:.0f} MiB per rank", flush=True)
+                      f"{total * 4 / 2**20:.0f} MiB per rank", file=sys.stderr, flush=True)
             return arena[:numel]
         except Exception as e:  # noqa: BLE001
             if dist.get_rank(self.pg) == 0:
-                print(f"[octcubem_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+                import sys
+                print(f"[octcubem_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr, flush=True)
             self._sym = None
             return None
 
