@@ -88,7 +88,7 @@ struct Cfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   // operand ring + 64 KB of output staging (+ 2 KB ones tile) within 227 KB
-  static constexpr int kStages = kPair ? (kColsum ? 4 : 5) : ((BLOCK_N == 256) ? 3 : (kColsum ? 4 : 5));
+  static constexpr int kStages = kPair ? (BLOCK_N == 256 ? (kColsum ? 4 : 5) : 6) : ((BLOCK_N == 256) ? 3 : (kColsum ? 4 : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAccStages = kColsum ? 1 : 2;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages, or one + the colsum columns (power of two: 256 or 512)
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   using C = Cfg<BLOCK_N, kColsum, kPair>;
   static_assert(!kColsum || A_MN, "the bias-gradient MMA sums the MN-major A operand over K");
   pdl_launch_dependents();
-  static_assert(!kPair || BLOCK_N == 256, "pair mode: 256 x 256 output tile per CTA pair");
+  static_assert(!kPair || BLOCK_N == 256 || (BLOCK_N == 128 && !kColsum), "pair mode: 256 x 256 (or 256 x 128) output tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ provenance (LDS/STS instead of generic LD/ST): offset the array, do not round-trip through an integer
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -561,14 +561,18 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   if (M == 0 || N == 0) return OCT_OK;
   OCT_REQUIRE(K > 0, "oct_gemm(bf16): K must be positive");
   const bool a_mn = (layout == OCT_GEMM_TN), b_mn = (layout != OCT_GEMM_NT);
-  const int block_n = (N > 128) ? 256 : 128;
+  int block_n = (N > 128) ? 256 : 128;
+  static const int force_bn = [] { const char* e = getenv("OCT_GEMM_BN"); return e ? atoi(e) : 0; }();  // experiment knob
+  if (force_bn == 128 || force_bn == 256) block_n = force_bn;
   CUtensorMap ta, tb;
   int rc = make_operand_map(&ta, A, a_mn, M, K, lda, BLOCK_M, "oct_gemm(bf16) A");
   if (rc) return rc;
   // pair mode (2-CTA clusters running cta_group::2 MMAs on 256 x 256 tiles) whenever there are at least two m-blocks
   // ... and the contraction is long enough for the main loop to matter: at K <= 512 (8 k-blocks per tile) the tile time is
   // the epilogue's, and the pair's cross-CTA accumulator hand-off only adds latency (tools/time_gemm_shapes.py)
-  const bool pair = (M > BLOCK_M) && block_n == 256 && K > 512 && (getenv("OCT_GEMM_NO_PAIR") == nullptr);
+  static const int pair_min_k = [] { const char* e = getenv("OCT_GEMM_PAIR_MIN_K"); return e ? atoi(e) : 512; }();
+  const bool pair = (M > BLOCK_M) && (block_n == 256 || (block_n == 128 && !colsum)) && K > pair_min_k &&
+                    (getenv("OCT_GEMM_NO_PAIR") == nullptr);
   rc = make_operand_map(&tb, B, b_mn, N, K, ldb, pair ? block_n / 2 : block_n, "oct_gemm(bf16) B");
   if (rc) return rc;
   // output maps for the TMA-store epilogue: [M, N] row-major, one box = 128 rows x 128 bytes
@@ -631,7 +635,7 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
     return block_n == 256 ? launch<true, true, 256, false, true>(ta, tb, td, tx, p, st) : launch<true, true, 128, false, true>(ta, tb, td, tx, p, st);
   }
 #define GO(AMN, BMN)                                                                                         \
-  if (pair) return launch<AMN, BMN, 256, true>(ta, tb, td, tx, p, st);                                   \
+  if (pair) return block_n == 256 ? launch<AMN, BMN, 256, true>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, true>(ta, tb, td, tx, p, st); \
   return block_n == 256 ? launch<AMN, BMN, 256, false>(ta, tb, td, tx, p, st) : launch<AMN, BMN, 128, false>(ta, tb, td, tx, p, st)
   switch (layout) {
     case OCT_GEMM_NT: GO(false, false);
