@@ -206,6 +206,12 @@ int oct_mean_pool_fwd(const void* x, int x_dtype, void* out, int out_dtype, int6
 int oct_mean_pool_bwd(const void* dout, int dout_dtype, void* dx, int dx_dtype, int64_t B, int64_t S, int64_t C, int64_t row0,
                       int64_t row1, oct_stream_t stream);
 
+/* ---- fixed sparse linear map on a table (ELL format): y[r,:] = sum_k w[r,k] * x[idx[r,k],:]  (fp32, fixed order) ----------
+ * The bicubic 32x32 -> 16x16 resampling of the learnable spatial pos tables (models:419-421, 537-539; F.interpolate bicubic,
+ * align_corners=False) is a fixed linear map with 16 taps per output cell; its transpose (the backward) has <= 9 per input cell.
+ * idx int32 [R,K], w f32 [R,K] (padding entries carry w = 0), x f32 [rows,C], y f32 [R,C]. */
+int oct_ell_spmm(const int* idx, const float* w, const float* x, float* y, int64_t R, int64_t K, int64_t C, oct_stream_t stream);
+
 /* ---- volume ingest: uint8 cube -> the step's fp32 input, replacing the loader's CPU work ------------------
  * dst [B,1,T,H,W] f32 <- src [B,T_src,H,W] u8 : value / divisor (ToTensor's /255, PatientDataset_inhouse.py:420), centre
  * zero-padding ((T - T_src) // 2 frames on the left) or centre cropping (frames [(T_src - T) // 2, ... + T)) to T frames

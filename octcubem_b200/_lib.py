@@ -55,6 +55,7 @@ SIGNATURES = {
     "oct_mean_pool_ws_bytes": (Z, [L, L, L, L]),
     "oct_mean_pool_fwd": (I, [P, I, P, I, L, L, L, L, L, P, Z, P]),
     "oct_mean_pool_bwd": (I, [P, I, P, I, L, L, L, L, L, P]),
+    "oct_ell_spmm": (I, [P, P, P, P, L, L, L, P]),
     "oct_ingest_u8": (I, [P, P, P, P, L, L, L, L, L, F, P]),
     "oct_fg_bbox_u8": (I, [P, P, L, L, L, L, P]),
     "oct_resize_trilinear_u8": (I, [P, P, P, L, L, L, L, L, L, L, I, I, F, P]),

@@ -430,10 +430,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   }
 }
 
-// delta[b,h,s] = sum_c dO[b,s,h,c] * O[b,s,h,c]   (one thread per (b,s,h) row: HD bf16 = 64 / 128 contiguous bytes)
+// delta[b,h,s] = sum_c dO[b,s,h,c] * O[b,s,h,c]   (one thread per (b,s,h) row: HD bf16 = 64 / 128 contiguous bytes).
+// The same thread clears the row's slot of the fp32 dQ accumulator (the drain warps of attn_bwd_tc_kernel reduce into it): a
+// separate memset was one more launch per layer (32 per step).  Rows s >= S of the padded accumulator are never read.
 template <int HD>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int64_t total, int S, int H) {
+                                  float* __restrict__ delta, float* __restrict__ dq_acc, int64_t total, int S, int H, int Spad) {
   pdl_launch_dependents();
   pdl_wait();
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,6 +456,12 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
   const int s = (int)(bs % S);
   const int64_t bb = bs / S;
   delta[(bb * H + hh) * S + s] = acc;
+  // accumulator layout per 128-query tile: [row quarter][16-byte chunk][32 rows][4 floats] (see the drain warps)
+  float* tile = dq_acc + ((bb * H + hh) * Spad + (s & ~127)) * HD;
+  const int rr = s & 127;
+#pragma unroll
+  for (int c4 = 0; c4 < HD / 4; ++c4)
+    *reinterpret_cast<float4*>(tile + (((rr >> 5) * (HD / 4) + c4) * 32 + (rr & 31)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // dq (bf16, into dqkv[:, :, 0]) = scale * dq_acc
@@ -498,11 +506,10 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if (rc) return rc;
   rc = make_map4(&md, dout, HD, H, S, B, "oct_attn_bwd(bf16) dout");
   if (rc) return rc;
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * H * Spad * HD * sizeof(float), st);
-  if (e != cudaSuccess) { oct_set_error("oct_attn_bwd(bf16): memset: %s", cudaGetErrorString(e)); return (int)e; }
+  cudaError_t e;
   const int64_t rows = B * S * H;
   oct_launch(attn_delta_kernel<HD>, dim3((unsigned)ceil_div64(rows, 256)), dim3(256), 0, st, 1, (const __nv_bfloat16*)out,
-             (const __nv_bfloat16*)dout, delta, rows, (int)S, (int)H);
+             (const __nv_bfloat16*)dout, delta, dq_acc, rows, (int)S, (int)H, (int)Spad);
   rc = oct_check_launch("oct_attn_bwd(bf16,delta)");
   if (rc) return rc;
   static bool attr_done = false;

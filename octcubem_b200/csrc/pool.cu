@@ -119,3 +119,38 @@ extern "C" int oct_mean_pool_bwd(const void* dout, int dout_dtype, void* dx, int
 #undef LAUNCH
   return oct_check_launch("oct_mean_pool_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse (ELL) matrix x dense table: y[r, :] = sum_k w[r, k] * x[idx[r, k], :]
+// The bicubic 32x32 -> 16x16 resampling of the learnable spatial pos tables (models:419-421, 537-539) is a FIXED linear map
+// with 16 taps per output cell (and its transpose, used by the backward, has at most 9 per input cell): as a dense fp32
+// CUDA-core GEMM it cost 52 us per call, four calls per step (profiles/r2_step_launches.md).  fp32, fixed summation order.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) ell_spmm_kernel(const int* __restrict__ idx, const float* __restrict__ w,
+                                                       const float* __restrict__ x, float* __restrict__ y, int K, int C) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const float wk = __ldg(w + (size_t)r * K + k);
+      if (wk != 0.f) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)__ldg(idx + (size_t)r * K + k) * C + c);
+        acc.x = fmaf(wk, v.x, acc.x); acc.y = fmaf(wk, v.y, acc.y); acc.z = fmaf(wk, v.z, acc.z); acc.w = fmaf(wk, v.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(y + (size_t)r * C + c) = acc;
+  }
+}
+}  // namespace
+
+extern "C" int oct_ell_spmm(const int* idx, const float* w, const float* x, float* y, int64_t R, int64_t K, int64_t C,
+                            oct_stream_t stream) {
+  OCT_REQUIRE(idx && w && x && y, "oct_ell_spmm: null pointer");
+  OCT_REQUIRE(R >= 0 && K >= 1 && C >= 4 && C % 4 == 0 && R < (1 << 30), "oct_ell_spmm: need K >= 1, C %% 4 == 0");
+  OCT_REQUIRE(aligned16(x) && aligned16(y), "oct_ell_spmm: x / y must be 16-byte aligned");
+  if (R == 0) return OCT_OK;
+  const int threads = (int)((C / 4 < 256) ? ((C / 4 + 31) / 32 * 32) : 256);
+  ell_spmm_kernel<<<(unsigned)R, threads, 0, (cudaStream_t)stream>>>(idx, w, x, y, (int)K, (int)C);
+  return oct_check_launch("oct_ell_spmm");
+}

@@ -228,7 +228,11 @@ class MaskedAutoencoderViT(nn.Module):
         hr_h, hr_w = self.high_res_input_size[1], self.high_res_input_size[2]
         eye = torch.eye(hr_h * hr_w).view(1, hr_h * hr_w, hr_h, hr_w)
         lo = F.interpolate(eye, [self.input_size[1], self.input_size[2]], mode="bicubic", align_corners=False)
-        self.register_buffer("_interp_mat", lo.reshape(hr_h * hr_w, -1).t().contiguous(), persistent=False)
+        mat = lo.reshape(hr_h * hr_w, -1).t().contiguous()                 # [G_lo, G_hi], 16 non-zeros per row
+        for name, t in zip(("_interp_idx", "_interp_w"), ops.ell_from_dense(mat)):
+            self.register_buffer(name, t, persistent=False)
+        for name, t in zip(("_interp_idx_t", "_interp_w_t"), ops.ell_from_dense(mat.t().contiguous())):
+            self.register_buffer(name, t, persistent=False)
         self.initialize_weights()
         self.set_precision(precision)
 
@@ -325,7 +329,7 @@ class MaskedAutoencoderViT(nn.Module):
         C = table.shape[-1]
         if high_res:
             return table.reshape(-1, C)
-        return ops.InterpTableFn.apply(table, self._interp_mat)
+        return ops.InterpTableFn.apply(table, self._interp_idx, self._interp_w, self._interp_idx_t, self._interp_w_t)
 
     def _is_high_res(self, H):
         return H == self.high_res_input_size[1] * self.high_res_patch_embed.patch_size[0]
