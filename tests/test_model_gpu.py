@@ -39,7 +39,7 @@ def test_toy_step_vs_reference_golden(golden_dir, precision, tol):
     assert np.array_equal(mask.cpu().numpy(), g["mask"])                      # bit-exact
     assert abs(float(loss) - float(g["loss"])) < tol * abs(float(g["loss"]))
     assert rel(fl, g["frame_losses"]) < tol
-    assert rel(pred.float(), g["pred"]) < (tol if precision == "fp32" else 3e-2)
+    assert rel(pred.float(), g["pred"]) < tol
     grads = {k: p.grad for k, p in m.named_parameters()}
     assert grads["high_res_patch_embed.proj.weight"] is None                 # quirk Q13
     worst = 0.0
@@ -47,7 +47,7 @@ def test_toy_step_vs_reference_golden(golden_dir, precision, tol):
         if k.startswith("g::"):
             r = rel(grads[k[3:]].float(), g[k])
             worst = max(worst, r)
-            assert r < (tol if precision == "fp32" else 5e-2), (k, r)
+            assert r < (tol), (k, r)
     print(f"worst grad rel err ({precision}): {worst:.2e}")
 
 
@@ -103,7 +103,7 @@ def test_joint_3d_plus_2d_step_vs_oracle(precision, tol):
     got = {k: p.grad for k, p in m.named_parameters()}
     assert all(v is not None for v in got.values()) and set(got) == set(want)
     for k in got:
-        assert rel(got[k], want[k]) < (tol if precision == "fp32" else 5e-2), k   # per-tensor bound of the toy-step test
+        assert rel(got[k], want[k]) < (tol), k   # per-tensor bound of the toy-step test
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
@@ -136,7 +136,7 @@ def test_joint_step_through_the_reducer_sinks(precision, tol):
         assert w.grad.data_ptr() == ops.grad_sinks[w.data_ptr()][0].data_ptr()       # produced in place
         got = {k: p.grad.clone() for k, p in m.named_parameters()}
         for k in got:
-            assert rel(got[k], want[k]) < (tol if precision == "fp32" else 5e-2), k
+            assert rel(got[k], want[k]) < (tol), k
         step()                                   # no zero_grad: accumulate
         for k, p in m.named_parameters():
             assert rel(p.grad, 2 * got[k]) < (1e-5 if precision == "fp32" else 2e-2), k
@@ -260,7 +260,7 @@ def test_full_size_gradients_vs_reference_golden(golden_dir, batch, precision):
                 worst_norm = (name, e)
             num += (got - want) ** 2
             den += want ** 2
-            assert e < (tol if precision == "fp32" else 3e-2), (name, got, want)
+            assert e < tol, (name, got, want)
     # (2) slices: element-wise agreement
     worst, over = ("", 0.0), []
     sq_err = sq_ref = 0.0
@@ -283,6 +283,6 @@ def test_full_size_gradients_vs_reference_golden(golden_dir, batch, precision):
     if precision == "fp32":
         assert not over, over
     else:
-        assert all(e < 5e-2 for _, e in over), over
+        assert not over, over      # measured worst per-tensor slice error: 1.45e-2 (blocks.23.mlp.fc2.weight)
     del m
     torch.cuda.empty_cache()
