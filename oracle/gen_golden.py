@@ -16,6 +16,7 @@ Fixtures:
                      volume, dlogits, reference logits / embedding / last hidden state / every parameter gradient.
   full_cfg1_grads.npz  ViT-L, 48x256x256, mask 0.9: reference loss + the norm of every parameter gradient + strided slices of 18
                      gradient tensors, for the first volume alone (cfg-1) and for the batch of 8 (cfg-2) (only with --full-grads).
+  full_cfg3_grads.npz  the same for ONE 60x256x256 volume (BASELINE cfg-3: L = 5120, keep = 511, S_dec = 5121).
   full_cfg1.json     ViT-L, 1x48x256x256, mask 0.9 (BASELINE cfg-1): reference loss / mask sum / pred stats
                      for oracle.init_state_dict(seed 0) weights (only with --full; ~1 min).
 """
@@ -190,6 +191,26 @@ def grad_slice(t, n=4096):
     return f[:: max(1, f.numel() // n)][:n]
 
 
+def gen_full_grads_cfg3():
+    """cfg-3 volume size (60x256x256: L = 5120, keep = 511 by Python's float truncation, S_dec = 5121), one volume: reference
+    loss, gradient norms and slices like gen_full_grads -> full_cfg3_grads.npz."""
+    cfg = O.MAEConfig(num_frames=60, pred_t_dim=60)
+    sd = O.init_state_dict(cfg, seed=0)
+    vol = O.synthetic_volume(1, 60, 256, 256, seed=0)
+    noise = O.synthetic_noise(1, cfg.t_grid * cfg.grid ** 2, seed=1)
+    m = R.build_reference(**cfg.ref_kwargs())
+    m.load_state_dict(sd, strict=True)
+    out = R.run_reference(m, vol, noise, 0.9, frame_loss=True, force_stable_argsort=True, backward=True)
+    rec = {"b1::loss": np.float64(float(out["loss"])), "b1::frame_losses": out["frame_losses"].detach().flatten().numpy(),
+           "mask_sum_per_volume": np.float64(float(out["mask"].sum()))}
+    for k, v in out["grads"].items():
+        rec["b1::norm::" + k] = np.float64(v.double().norm())
+        if k in GRAD_SLICE_TENSORS:
+            rec["b1::slice::" + k] = grad_slice(v).float().numpy()
+    np.savez_compressed(os.path.join(GOLD, "full_cfg3_grads.npz"), **rec)
+    print("full_cfg3_grads.npz: loss", rec["b1::loss"], "mask sum", rec["mask_sum_per_volume"])
+
+
 def gen_full_grads(batch=8):
     """Reference GRADIENTS at production size (ViT-L, 48x256x256, mask 0.9, fp32 CPU): cfg-1 (the first volume alone) and a
     batch of `batch` volumes (BASELINE cfg-2's batch).  The reference is run once per volume — its softmax(QK^T) at S = 4097
@@ -241,13 +262,19 @@ def gen_full_grads(batch=8):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--full-grads", action="store_true", help="full_cfg1_grads.npz only (reference fwd+bwd at production size; ~10 min)")
+    ap.add_argument("--full-grads", action="store_true", help="full_cfg1_grads.npz + full_cfg3_grads.npz (reference fwd+bwd at production size; ~10 min)")
+    ap.add_argument("--full-grads-cfg3", action="store_true", help="full_cfg3_grads.npz only (60-frame volume)")
     ap.add_argument("--only-2d", action="store_true", help="regenerate toy2d_step.npz only")
     ap.add_argument("--only-vit", action="store_true", help="regenerate toy_vit_step.npz only")
     a = ap.parse_args()
     if a.full_grads:
         torch.set_num_threads(os.cpu_count())
         gen_full_grads()
+        gen_full_grads_cfg3()
+        sys.exit(0)
+    if a.full_grads_cfg3:
+        torch.set_num_threads(os.cpu_count())
+        gen_full_grads_cfg3()
         sys.exit(0)
     if a.only_2d:
         gen_toy2d()

@@ -212,31 +212,33 @@ def test_full_cfg1_loss_vs_reference_golden(golden_dir):
         torch.cuda.empty_cache()
 
 
-def _full_model_and_inputs(batch):
-    cfg = O.MAEConfig(num_frames=48, pred_t_dim=48)
+def _full_model_and_inputs(batch, frames=48):
+    cfg = O.MAEConfig(num_frames=frames, pred_t_dim=frames)
     sd = O.init_state_dict(cfg, seed=0)
-    vol, noise = O.synthetic_volume(batch, 48, 256, 256, seed=0), O.synthetic_noise(batch, 4096, seed=1)
+    L = (frames // 3) * 256
+    vol, noise = O.synthetic_volume(batch, frames, 256, 256, seed=0), O.synthetic_noise(batch, L, seed=1)
     return cfg, sd, vol, noise
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("batch", [1, 8])
+@pytest.mark.parametrize("batch,frames", [(1, 48), (8, 48), (1, 60)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_full_size_gradients_vs_reference_golden(golden_dir, batch, precision):
+def test_full_size_gradients_vs_reference_golden(golden_dir, batch, frames, precision):
     """Production dims (ViT-L, 16x64 / 16x32 heads, S_enc = 410, S_dec = 4097 — the head_dim 64 tcgen05 attention, the
     cta_group::2 pair GEMMs, the single-live-row tail CTA all run THROUGH THE MODULE here), cfg-1 (one volume) and the cfg-2
     batch of 8: loss, frame losses, the norm of EVERY parameter gradient and strided slices of 18 gradient tensors against the
-    unmodified reference's fp32 CPU step (tests/golden/full_cfg1_grads.npz, oracle/gen_golden.py --full-grads).
+    unmodified reference's fp32 CPU step (tests/golden/full_cfg1_grads.npz; full_cfg3_grads.npz = one 60-frame volume, cfg-3:
+    L = 5120, keep = 511, S_dec = 5121; oracle/gen_golden.py --full-grads).
     fp32: 1e-4 everywhere.  bf16: loss and whole-gradient norm-weighted error within 2e-2; per-tensor slices within 2e-2 or
     listed (tiny-magnitude tensors whose bf16 rounding error the reference's own bf16 stack shares, see
     tests/test_incumbent_gpu.py and profiles/r2_parity.md)."""
     from oracle.gen_golden import grad_slice
-    path = os.path.join(golden_dir, "full_cfg1_grads.npz")
+    path = os.path.join(golden_dir, "full_cfg1_grads.npz" if frames == 48 else "full_cfg3_grads.npz")
     if not os.path.isfile(path):
-        pytest.skip("full_cfg1_grads.npz not generated")
+        pytest.skip(os.path.basename(path) + " not generated")
     g = np.load(path)
     tag = f"b{batch}::"
-    cfg, sd, vol, noise = _full_model_and_inputs(batch)
+    cfg, sd, vol, noise = _full_model_and_inputs(batch, frames)
     m = build(cfg, sd, precision)
     (loss, fl), pred, mask = m(vol.to(DEV), mask_ratio=0.9, frame_loss=True, noise=noise.to(DEV))
     loss.backward()
@@ -277,7 +279,7 @@ def test_full_size_gradients_vs_reference_golden(golden_dir, batch, precision):
             if e >= tol:
                 over.append((name, round(e, 4)))
     pooled = (sq_err / sq_ref) ** 0.5
-    print(f"[{precision} B={batch}] loss {float(loss):.6f} vs {float(g[tag + 'loss']):.6f}; worst norm err {worst_norm}; "
+    print(f"[{precision} B={batch} T={frames}] loss {float(loss):.6f} vs {float(g[tag + 'loss']):.6f}; worst norm err {worst_norm}; "
           f"worst slice err {worst}; pooled slice err {pooled:.2e}; over tol: {over}")
     assert pooled < tol
     if precision == "fp32":
