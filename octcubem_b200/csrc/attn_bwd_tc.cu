@@ -35,6 +35,15 @@ constexpr int AB_T = 128, AB_SUB = 64, AB_THREADS = 512, AB_SM_THREADS = 256, AB
 // register budget (setmaxnreg, per warpgroup): 8 softmax warps x 176 + 8 control / drain warps x 80 = 64 K registers
 constexpr int AB_REGS_SOFTMAX = 176, AB_REGS_OTHER = 80;
 constexpr float kLog2e = 1.4426950408889634f;
+#ifndef AB_NS32   // experiment knobs (tools/build_variant.sh): score stages / alternating softmax groups at head_dim 32
+#define AB_NS32 3
+#endif
+#ifndef AB_ALT32
+#define AB_ALT32 1
+#endif
+#ifndef AB_KNOCK  // timing experiments ONLY (results are wrong): 1 no exponentials, 2 no dS^T st.shared, 4 no dQ MMAs, 8 no G MMAs,
+#define AB_KNOCK 0  // 16 no tcgen05.st of P^T / dS^T, 32 no tcgen05.ld of the scores, 64 no S/dP MMAs
+#endif
 
 template <int HD>
 struct AbCfg {
@@ -49,10 +58,20 @@ struct AbCfg {
   // is ONE sub-tile (~1400 clk) before the issuer needs the data, less than a TMA round trip: the clock64 trace showed the
   // issuer waiting ~1100 clk for q_full at every second sub-tile (38 % of the kernel).  head_dim 64 has no room for more.
   static constexpr int kQStages = (HD == 32) ? 4 : 2;
-  static constexpr int kSmem = 2 * kTileBytes + 2 * kQStages * kTileBytes + 2 * kDsBytes + kDqBytes + 8 * 2 * 64 * 4 + 1024 + 256;
+  // fp32 score stages in TMEM.  head_dim 32 has room for three (3 x 128 + 96 columns): the scores of sub-tile i + 3 are
+  // queued behind the gradient MMAs of sub-tile i, so a softmax group that finishes sub-tile i finds S/dP(i + 2) complete
+  // instead of waiting for its own p_ready -> issuer -> tensor pipe round trip.
+  static constexpr int kNS = (HD == 32) ? AB_NS32 : 2;
+  // kAlt: the two softmax warps of a scheduler work on DIFFERENT sub-tiles (group g = warp >> 2 owns the sub-tiles
+  // i = g mod 2, all 64 query columns) instead of on the two column halves of the same one.  In the column-split form both
+  // warps wait on the same barrier and run in phase: their exponentials contend for the MUFU (512 clk for the pair) and
+  // then BOTH sit in the TMEM store / fence / barrier tail with the MUFU idle (~1230 clk per sub-tile, clock64 trace).
+  static constexpr bool kAlt = (HD == 32) && (AB_ALT32 != 0);
+  static constexpr int kStatFloats = kQStages * 256;  // per Q/dO ring stage: [128 x -lse*log2e | 128 x -delta] of the query tile
+  static constexpr int kSmem = 2 * kTileBytes + 2 * kQStages * kTileBytes + 2 * kDsBytes + kDqBytes + kStatFloats * 4 + 1024 + 512;
   // TMEM columns: stage s of the fp32 sub-tiles: S^T at 128 s, dP^T at 128 s + 64; accumulators behind them
   static constexpr uint32_t kColST = 0, kColDPT = 64, kStageCols = 128;
-  static constexpr uint32_t kColDV = 256, kColDK = 256 + HD, kColDQ = 256 + 2 * HD;
+  static constexpr uint32_t kColDV = kNS * 128, kColDK = kNS * 128 + HD, kColDQ = kNS * 128 + 2 * HD;
   static_assert(kColDQ + HD <= 512, "TMEM budget");
   // bf16 K-slice k (16 queries, 8 columns) of a sub-tile: the warp that owns query columns [32 c, 32 c + 32) writes its
   // bf16 output over its own fp32 columns -> slices 0,1 at columns 0,8 and slices 2,3 at columns 32,40
@@ -62,8 +81,8 @@ struct AbCfg {
 struct AbParams {
   int S, H, Spad;
   float scale, scale_log2e;
-  const float* lse;     // [B,H,S]
-  const float* delta;   // [B,H,S]
+  const float* nlse2;   // [B,H,Spad]  -lse * log2(e)  (-inf for s >= S), written by attn_delta_kernel
+  const float* ndelta;  // [B,H,Spad]  -delta          (0 for s >= S)
   float* dq_acc;        // [B,H,Spad/128][lane quarter][HD/4 chunks][32 rows][4] fp32, zero-initialised (see the drain warps)
   __nv_bfloat16* dqkv;  // [B,S,3,H,HD]
   int dbg;              // OCT_ATTN_BWD_DBG=16: record a cycle trace of CTA (1,0,0) (diagnostics only)
@@ -80,15 +99,21 @@ struct AbParams {
 #else
 #define AB_WAIT tc::mbar_wait
 #endif
-__device__ long long g_ab_trace[8 * 16];
+__device__ long long g_ab_trace[8 * 48];
 #if !OCT_AB_TRACE
 #define AB_TRACE(id) do {} while (0)
+#define AB_TRACEW(id) do {} while (0)
 #else
 #define AB_TRACE(id)                                                                                              \
   do {                                                                                                           \
-    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 9 || warp == 0) && \
+    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp >= 9 && warp <= 11 || warp == 0 || (C::kAlt && warp == 4)) && \
         i >= 8 && i < 16)                                                                                        \
-      g_ab_trace[(i - 8) * 16 + (id)] = clock64();                                                               \
+      g_ab_trace[(i - 8) * 48 + (id)] = clock64();                                                               \
+  } while (0)
+#define AB_TRACEW(id)                                                                                             \
+  do {                                                                                                           \
+    if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && i >= 8 && i < 16)   \
+      g_ab_trace[(i - 8) * 48 + 16 + 4 * warp + (id)] = clock64();                                                \
   } while (0)
 #endif
 
@@ -107,14 +132,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint8_t* sDO = sQ + C::kQStages * C::kTileBytes;        // [C::kQStages]
   uint8_t* sDS = sDO + C::kQStages * C::kTileBytes;       // [2] x 32 KB, 1024-aligned (all tiles are multiples of 8 KB)
   uint8_t* sDQ = sDS + 2 * C::kDsBytes;                   // [128][HD] fp32, swizzled
-  float* sStat = reinterpret_cast<float*>(sDQ + C::kDqBytes);  // [8 warps][2 slots][32 x -lse*log2e | 32 x -delta]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 8 * 2 * 64);
+  float* sStat = reinterpret_cast<float*>(sDQ + C::kDqBytes);  // [kQStages][128 x -lse*log2e | 128 x -delta], filled by the producer
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + C::kStatFloats);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;                 // [2]
   uint64_t* q_empty = q_full + C::kQStages;    // [2]
-  uint64_t* sdp_full = q_empty + C::kQStages;  // [2] per fp32 stage, one completion every other sub-tile
-  uint64_t* p_ready = sdp_full + 2;            // [2] per fp32 stage (256 arrivals)
-  uint64_t* dq_full = p_ready + 2;             // once per query tile
+  uint64_t* sdp_full = q_empty + C::kQStages;  // [kNS] per fp32 stage, one completion every kNS sub-tiles
+  uint64_t* p_ready = sdp_full + C::kNS;       // [kNS] per fp32 stage (one arrival per softmax warp that worked on it)
+  uint64_t* g_done = p_ready + C::kNS;         // [kNS] G(i) complete: the stage may receive the scores of sub-tile i + kNS
+  uint64_t* ds_ready = g_done + C::kNS;        // [2] per dS^T buffer: both 64-query chunks written (softmax warps of two sub-tiles)
+  uint64_t* ds_free = ds_ready + 2;            // [2] per dS^T buffer: dQ_m has read it
+  uint64_t* dq_full = ds_free + 2;             // once per query tile
   uint64_t* dq_free = dq_full + 1;             // once per query tile (the 128 drain threads)
   uint64_t* acc_full = dq_free + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -132,7 +160,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     tc::prefetch_tmap(&tmap_do);
     tc::mbar_init(kv_full, 1);
     for (int s = 0; s < C::kQStages; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&sdp_full[s], 1); tc::mbar_init(&p_ready[s], AB_SM_THREADS); }
+    for (int s = 0; s < C::kNS; ++s) {
+      tc::mbar_init(&sdp_full[s], 1);
+      tc::mbar_init(&p_ready[s], C::kAlt ? 4 : 8);
+      tc::mbar_init(&g_done[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&ds_ready[s], C::kAlt ? 8 : 16); tc::mbar_init(&ds_free[s], 1); }
     tc::mbar_init(dq_full, 1);
     tc::mbar_init(dq_free, AB_DRAIN_THREADS);
     tc::mbar_init(acc_full, 1);
@@ -163,104 +196,121 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       int stage = 0; uint32_t phase = 0;
       for (int m = 0; m < n_q; ++m) {
         tc::mbar_wait(&q_empty[stage], phase ^ 1);
-        tc::mbar_arrive_expect_tx(&q_full[stage], 2 * C::kTileBytes);
+        tc::mbar_arrive_expect_tx(&q_full[stage], 2 * C::kTileBytes + 2 * AB_T * 4);
         tc::tma_load_4d(sQ + stage * C::kTileBytes, &tmap_qkv, &q_full[stage], 0, h, m * AB_T, b);
         tc::tma_load_4d(sDO + stage * C::kTileBytes, &tmap_do, &q_full[stage], 0, h, m * AB_T, b);
+        // the tile's softmax statistics ride in the same ring stage: per-thread global loads + an smem staging round per
+        // sub-tile cost the softmax warps ~500 clk of their ~1800 clk period (clock64 trace; -10 % kernel time without the loads)
+        const size_t srow = ((size_t)b * p.H + h) * p.Spad + (size_t)m * AB_T;
+        tc::bulk_load_1d(sStat + stage * 256, p.nlse2 + srow, AB_T * 4, &q_full[stage]);
+        tc::bulk_load_1d(sStat + stage * 256 + 128, p.ndelta + srow, AB_T * 4, &q_full[stage]);
         if (++stage == C::kQStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    // The whole warp runs the loop and the barrier waits; MMAs / commits are issued under elect.sync.  Inside a
-    // `lane == 0` branch ptxas wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop (attn_tc.cu has the numbers).
-    {
-      constexpr uint32_t idesc_st = tc::make_idesc(tc::kFmtBF16, false, false, 128, AB_SUB);  // K Q_h^T, V dO_h^T
+  } else if (warp == 9 || warp == 10 || warp == 11) {
+    // ===================== three MMA issuers =====================
+    // One warp issuing everything executed ~200 instructions per sub-tile (three barrier waits, descriptor arithmetic in
+    // uniform registers, 16-24 MMAs, commits) in ONE dependent stream: ~600 clk per sub-tile on top of the ~620 clk its
+    // MMAs keep the tensor pipe busy, with the pipe idle during the former (clock64 trace, profiles/r2_attention_ncu.md).
+    // The three MMA families have different producers and consumers, so each gets its own warp and its own barriers:
+    //   warp 9   G(i):    dV += P^T dO_h, dK += dS^T Q_h    after p_ready[st]          -> g_done[st], q_empty, acc_full
+    //   warp 10  dQ(m):   dQ_m = dS K                       after ds_ready[m&1], dq_free -> dq_full, ds_free[m&1]
+    //   warp 11  S/dP(j): S^T = K Q_h^T, dP^T = V dO_h^T    after g_done[st] (G(j - kNS) has read the stage's bf16 contents),
+    //                     q_full, ds_free (dQ of query tile (j>>1) - 2 has read the dS^T buffer the softmax warps of
+    //                     sub-tile j are about to overwrite)                            -> sdp_full[st]
+    // tcgen05.commit only covers the MMAs of the committing thread; every cross-warp ordering goes through one of the
+    // barriers above.  Each warp runs its loop and waits with all lanes; MMAs / commits are issued under elect.sync
+    // (inside a `lane == 0` branch ptxas wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop, attn_tc.cu).
+    constexpr uint32_t kStageStep = C::kTileBytes >> 4, kHalfStep = (AB_SUB * C::kRowBytes) >> 4;
+    constexpr uint32_t kKStepK = 32 >> 4, kKStepMN = (16 * C::kRowBytes) >> 4, kKStepDS = (16 * 128) >> 4;
+    constexpr uint32_t kDsBufStep = C::kDsBytes >> 4;
+    // Descriptors are built once; inside the loops only their 14-bit start-address field (units of 16 B) is advanced.
+    if (warp == 9) {
       constexpr uint32_t idesc_acc = tc::make_idesc(tc::kFmtBF16, false, true, 128, HD);       // P^T dO_h, dS^T Q_h (TS)
-      constexpr uint32_t idesc_dq = tc::make_idesc(tc::kFmtBF16, true, true, 128, HD);         // dS K (A MN-major)
-      const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV), ds_addr = tc::smem_u32(sDS);
-      // Descriptors are built once; inside the loop only their 14-bit start-address field (units of 16 B) is advanced.
-      const uint64_t dK_kmaj = tc::make_smem_desc(k_addr, 16, C::kSBO, C::kSwz);                 // K as K-major A
-      const uint64_t dV_kmaj = tc::make_smem_desc(v_addr, 16, C::kSBO, C::kSwz);                 // V as K-major A
-      const uint64_t dK_mn = tc::make_smem_desc(k_addr, C::kTileBytes, C::kSBO, C::kSwz);        // K as MN-major B (dQ)
-      const uint64_t dDS_mn = tc::make_smem_desc(ds_addr, 128 * 128, 1024, tc::kSwz128);         // dS^T as MN-major A (dQ)
-      const uint64_t dQ0_kmaj = tc::make_smem_desc(tc::smem_u32(sQ), 16, C::kSBO, C::kSwz);      // stage 0, half 0
-      const uint64_t dDO0_kmaj = tc::make_smem_desc(tc::smem_u32(sDO), 16, C::kSBO, C::kSwz);
       const uint64_t dQ0_mn = tc::make_smem_desc(tc::smem_u32(sQ), C::kTileBytes, C::kSBO, C::kSwz);
       const uint64_t dDO0_mn = tc::make_smem_desc(tc::smem_u32(sDO), C::kTileBytes, C::kSBO, C::kSwz);
-      constexpr uint32_t kStageStep = C::kTileBytes >> 4, kHalfStep = (AB_SUB * C::kRowBytes) >> 4;
-      constexpr uint32_t kKStepK = 32 >> 4, kKStepMN = (16 * C::kRowBytes) >> 4, kKStepDS = (16 * 128) >> 4;
-      constexpr uint32_t kDsBufStep = C::kDsBytes >> 4;
-      // sub-tile j -> (q tile j>>1, half j&1); its Q/dO ring stage is (j>>1) % C::kQStages, its fp32 stage is j&1
-      auto wait_q = [&](int j) {  // all lanes: first use of Q/dO tile j >> 1
-        if ((j & 1) == 0) {
-          tc::mbar_wait(&q_full[(j >> 1) % C::kQStages], ((j >> 1) / C::kQStages) & 1);
-          tc::tcgen05_fence_after();
-        }
-      };
-      auto issue_sdp = [&](int j) {  // elected lane: S^T = K Q_h^T ; dP^T = V dO_h^T into fp32 stage j&1
-        const int qstage = (j >> 1) % C::kQStages;
-        const uint32_t off = qstage * kStageStep + (j & 1) * kHalfStep;
-        const uint32_t tcol = tmem_base + (j & 1) * C::kStageCols;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::mma_ss(tcol + C::kColST, dK_kmaj + k * kKStepK, dQ0_kmaj + off + k * kKStepK, idesc_st, k != 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::mma_ss(tcol + C::kColDPT, dV_kmaj + k * kKStepK, dDO0_kmaj + off + k * kKStepK, idesc_st, k != 0);
-        tc::mma_commit(&sdp_full[j & 1]);
-      };
-      tc::mbar_wait(kv_full, 0);
-      wait_q(0);
-      if (tc::elect_one()) {
-        issue_sdp(0);
-        if (n_sub > 1) issue_sdp(1);
-      }
-      __syncwarp();
       for (int i = 0; i < n_sub; ++i) {
-        const int m = i >> 1, hh = i & 1, st = i & 1;
-        const int qstage = m % C::kQStages;
-        const uint32_t off = qstage * kStageStep + hh * kHalfStep;
+        const int m = i >> 1, hh = i & 1, st = i % C::kNS;
+        const uint32_t off = (m % C::kQStages) * kStageStep + hh * kHalfStep;
         const uint32_t tcol = tmem_base + st * C::kStageCols;
         AB_TRACE(0);
-        // This warp is the critical path once the softmax warps have slack (clock64 trace: ~45-65 clk per issued MMA,
-        // the tensor pipe streams a 128x16 A operand per instruction whatever N is): all waits first, then ONE elected
-        // region.  Order G(i) -> S/dP(i+2) -> dQ(m): the scores the softmax warps wait for are not queued behind dQ,
-        // which only the drain warps need.
-        const bool dq_now = (hh == 1) || (i == n_sub - 1);
-        AB_WAIT(&p_ready[st], (i >> 1) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM, dS^T chunk hh in smem
-        AB_TRACE(10);
-        if (i + 2 < n_sub) wait_q(i + 2);
-        AB_TRACE(11);
-        if (dq_now && m > 0) tc::mbar_wait(dq_free, (m - 1) & 1);  // previous dQ tile drained from TMEM (long ago)
+        AB_WAIT(&p_ready[st], (i / C::kNS) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM
         tc::tcgen05_fence_after();
         AB_TRACE(1);
         if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AB_SUB / 16; ++k)  // dV += P^T dO_h
+          for (int k = 0; k < ((AB_KNOCK & 8) ? 0 : AB_SUB / 16); ++k)  // dV += P^T dO_h
             tc::mma_ts(tmem_base + C::kColDV, tcol + C::kColST + C::slice_off(k), dDO0_mn + off + k * kKStepMN, idesc_acc,
                        (i | k) != 0);
 #pragma unroll
-          for (int k = 0; k < AB_SUB / 16; ++k)  // dK += dS^T Q_h
+          for (int k = 0; k < ((AB_KNOCK & 8) ? 0 : AB_SUB / 16); ++k)  // dK += dS^T Q_h
             tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
                        (i | k) != 0);
-          if (dq_now) tc::mma_commit(&q_empty[qstage]);  // Q_m / dO_m fully consumed (sdp of both halves issued earlier)
-          // scores of sub-tile i+2 reuse fp32 stage st: queued behind the MMAs above, which read its bf16 contents
-          if (i + 2 < n_sub) issue_sdp(i + 2);
-          AB_TRACE(2);
-          if (dq_now) {
-            const uint32_t dsoff = (m & 1) * kDsBufStep;
-#pragma unroll
-            for (int k = 0; k < 128 / 16; ++k)  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
-              tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + dsoff + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
-            tc::mma_commit(dq_full);
-          }
+          tc::mma_commit(&g_done[st]);
+          // Q_m / dO_m fully consumed: this G is causally after S/dP of both halves (p_ready <- softmax <- sdp_full)
+          if (hh == 1 || i == n_sub - 1) tc::mma_commit(&q_empty[m % C::kQStages]);
         }
         __syncwarp();
         AB_TRACE(3);
       }
       if (tc::elect_one()) tc::mma_commit(acc_full);
+      __syncwarp();
+    } else if (warp == 10) {
+      constexpr uint32_t idesc_dq = tc::make_idesc(tc::kFmtBF16, true, true, 128, HD);         // dS K (A MN-major)
+      const uint64_t dK_mn = tc::make_smem_desc(tc::smem_u32(sK), C::kTileBytes, C::kSBO, C::kSwz);          // K as MN-major B
+      const uint64_t dDS_mn = tc::make_smem_desc(tc::smem_u32(sDS), 128 * 128, 1024, tc::kSwz128);           // dS^T as MN-major A
+      tc::mbar_wait(kv_full, 0);
+      for (int m = 0; m < n_q; ++m) {
+        [[maybe_unused]] const int i = 2 * m + 1;                 // (trace slot)
+        AB_WAIT(&ds_ready[m & 1], (m >> 1) & 1);            // both 64-query chunks of dS^T(m) are in smem
+        if (m > 0) tc::mbar_wait(dq_free, (m - 1) & 1);           // previous dQ tile drained from TMEM
+        tc::tcgen05_fence_after();
+        AB_TRACE(12);
+        if (tc::elect_one()) {
+          const uint32_t dsoff = (m & 1) * kDsBufStep;
+#pragma unroll
+          for (int k = 0; k < ((AB_KNOCK & 4) ? 0 : 128 / 16); ++k)  // dQ_m = dS K : A = dS^T smem tile read MN-major (M = q contiguous)
+            tc::mma_ss(tmem_base + C::kColDQ, dDS_mn + dsoff + k * kKStepDS, dK_mn + k * kKStepMN, idesc_dq, k != 0);
+          tc::mma_commit(dq_full);
+          tc::mma_commit(&ds_free[m & 1]);
+        }
+        __syncwarp();
+        AB_TRACE(13);
+      }
+    } else {
+      constexpr uint32_t idesc_st = tc::make_idesc(tc::kFmtBF16, false, false, 128, AB_SUB);  // K Q_h^T, V dO_h^T
+      const uint64_t dK_kmaj = tc::make_smem_desc(tc::smem_u32(sK), 16, C::kSBO, C::kSwz);       // K as K-major A
+      const uint64_t dV_kmaj = tc::make_smem_desc(tc::smem_u32(sV), 16, C::kSBO, C::kSwz);       // V as K-major A
+      const uint64_t dQ0_kmaj = tc::make_smem_desc(tc::smem_u32(sQ), 16, C::kSBO, C::kSwz);      // stage 0, half 0
+      const uint64_t dDO0_kmaj = tc::make_smem_desc(tc::smem_u32(sDO), 16, C::kSBO, C::kSwz);
+      tc::mbar_wait(kv_full, 0);
+      // sub-tile j -> (q tile j>>1, half j&1); its Q/dO ring stage is (j>>1) % C::kQStages, its fp32 stage is j % kNS
+      for (int j = 0; j < n_sub; ++j) {
+        const int st = j % C::kNS, t = j >> 1;
+        [[maybe_unused]] const int i = j;
+        AB_TRACE(10);
+        if (j >= C::kNS) AB_WAIT(&g_done[st], ((j - C::kNS) / C::kNS) & 1);
+        if ((j & 1) == 0) {
+          tc::mbar_wait(&q_full[t % C::kQStages], (t / C::kQStages) & 1);   // first use of Q/dO tile t
+          if (t >= 2) tc::mbar_wait(&ds_free[t & 1], ((t - 2) >> 1) & 1);   // dQ(t - 2) has read the dS^T buffer of tile t
+        }
+        tc::tcgen05_fence_after();
+        AB_TRACE(11);
+        if (tc::elect_one()) {
+          const uint32_t off = (t % C::kQStages) * kStageStep + (j & 1) * kHalfStep;
+          const uint32_t tcol = tmem_base + st * C::kStageCols;
+#pragma unroll
+          for (int k = 0; k < ((AB_KNOCK & 64) ? 0 : HD / 16); ++k)
+            tc::mma_ss(tcol + C::kColST, dK_kmaj + k * kKStepK, dQ0_kmaj + off + k * kKStepK, idesc_st, k != 0);
+#pragma unroll
+          for (int k = 0; k < ((AB_KNOCK & 64) ? 0 : HD / 16); ++k)
+            tc::mma_ss(tcol + C::kColDPT, dV_kmaj + k * kKStepK, dDO0_kmaj + off + k * kKStepK, idesc_st, k != 0);
+          tc::mma_commit(&sdp_full[st]);
+        }
+        __syncwarp();
+        AB_TRACE(2);
+      }
     }
-    __syncwarp();
   }
   } else if (warp >= 12) {
     // ===================== dQ drain: warp 12 + q owns TMEM lane quarter q =====================
@@ -293,7 +343,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         *reinterpret_cast<uint4*>(sdq_w + (q * 32 + lane) * 16) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       tc::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(AB_KNOCK & 128)) {
         float* dst = p.dq_acc + (bh * p.Spad + (size_t)m * AB_T) * HD + quarter * (kWarpDqBytes / 4);
         asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
                      "r"(tc::smem_u32(sdq_w)), "r"((uint32_t)kWarpDqBytes)
@@ -301,99 +351,113 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read; visibility = kernel boundary
   } else {
-    // ===================== softmax-backward threads: (kv row, 32 query columns) per sub-tile =====================
+    // ===================== softmax-backward threads =====================
+    // column-split form: (kv row, 32 query columns) of EVERY sub-tile; kAlt: (kv row, 64 query columns) of every OTHER one
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AB_REGS_SOFTMAX));
-    const int quarter = warp & 3, colhalf = warp >> 2;
+    const int quarter = warp & 3, colhalf = warp >> 2;  // kAlt: colhalf is the GROUP (parity of the sub-tiles it owns)
     const int row = quarter * 32 + lane;  // kv row inside the tile == TMEM lane
     const bool kv_ok = (n0 + row) < p.S;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const size_t bh = (size_t)b * p.H + h;
-    // The eight warps never synchronise with each other (only through p_ready -> the MMA issuer): each warp stages the
-    // statistics of ITS 32 query columns and drains ITS 32 x HD/2 block of dQ.  CTA-wide bar.syncs here cost ~900 clk
-    // per query tile in warp skew (clock64 trace, profiles/r1_attention_ncu.md).
-    // per-query statistics of this warp's columns of a sub-tile, fetched one sub-tile ahead (raw; transformed when stored)
-    auto stat_q = [&](int i) { return (i >> 1) * AB_T + (i & 1) * AB_SUB + colhalf * 32 + lane; };
-    auto ld_stat = [&](int i, float& a, float& d) {
-      const size_t idx = bh * p.S + min(stat_q(i), p.S - 1);
-      a = p.lse[idx];
-      d = p.delta[idx];
-    };
-    float raw_lse, raw_delta;
-    ld_stat(0, raw_lse, raw_delta);
-    for (int i = 0; i < n_sub; ++i) {
-      const int m = i >> 1, hh = i & 1, st = i & 1;
-      float* stat = sStat + warp * 128 + (i & 1) * 64;  // slot last read two sub-tiles ago by this same warp
-      {
-        const bool ok = stat_q(i) < p.S;
-        stat[lane] = ok ? -raw_lse * kLog2e : -INFINITY;  // negated, log2 domain: x = s * scale + stat
-        stat[32 + lane] = ok ? -raw_delta : 0.f;          // negated: dP + (-delta) is one FADD2
-        __syncwarp();
-        if (i + 1 < n_sub) ld_stat(i + 1, raw_lse, raw_delta);
-      }
-      const uint32_t tcol = lane_addr + st * C::kStageCols + colhalf * 32;
+    constexpr int kNC = C::kAlt ? 2 : 1;  // 32-column halves per warp and sub-tile
+    // The eight warps never synchronise with each other (only through p_ready -> the MMA issuers).  The per-query statistics
+    // (-lse log2e, -delta; masked for s >= S by attn_delta_kernel) arrive with the query tile in its ring stage.
+    const int i_first = C::kAlt ? colhalf : 0, i_step = C::kAlt ? 2 : 1;
+    for (int i = i_first; i < n_sub; i += i_step) {
+      const int m = i >> 1, hh = i & 1, st = i % C::kNS;
+      const float* stat = sStat + (m % C::kQStages) * 256 + hh * AB_SUB;
+      // the stage's bulk copies completed on q_full (long ago: the S/dP issuer waited for it before the scores of this
+      // sub-tile were queued); observing the phase here makes their bytes visible to this thread
+      tc::mbar_wait(&q_full[m % C::kQStages], (m / C::kQStages) & 1);
       AB_TRACE(4);
-      AB_WAIT(&sdp_full[st], (i >> 1) & 1);
+      AB_TRACEW(2);
+      AB_WAIT(&sdp_full[st], (i / C::kNS) & 1);
       tc::tcgen05_fence_after();
       AB_TRACE(5);
-      uint32_t s[32], dp[32];
-      tc::tmem_ld_x32(tcol + C::kColST, s);
-      tc::tmem_ld_x32(tcol + C::kColDPT, dp);
-      tc::tmem_ld_wait();
-      AB_TRACE(6);
-      uint32_t pk[16], dk[16];
-      const float4* l4 = reinterpret_cast<const float4*>(stat);
-      const float4* d4 = reinterpret_cast<const float4*>(stat + 32);
+      AB_TRACEW(0);
       // Packed fp32x2 math (FFMA2 / FADD2 / FMUL2): half the issue slots around the exponentials.  No masking is
       // needed: query columns past S carry lse = +inf (P = 0), and kv rows past S have zero-filled K / V rows, so
       // their (finite) P and dS only reach dV / dK rows that are never stored and add dS * 0 to dQ.
       const uint64_t sc2 = tc::pack2(p.scale_log2e, p.scale_log2e);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 lv = l4[q], dv = d4[q];
-        const uint64_t xa = tc::fma2(tc::pack2(__uint_as_float(s[4 * q]), __uint_as_float(s[4 * q + 1])), sc2,
-                                     tc::pack2(lv.x, lv.y));
-        const uint64_t xb = tc::fma2(tc::pack2(__uint_as_float(s[4 * q + 2]), __uint_as_float(s[4 * q + 3])), sc2,
-                                     tc::pack2(lv.z, lv.w));
-        float x0, x1, x2, x3;
-        tc::unpack2(xa, x0, x1);
-        tc::unpack2(xb, x2, x3);
-        const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1), p2 = tc::fast_exp2(x2), p3 = tc::fast_exp2(x3);
-        const uint64_t da = tc::mul2(tc::pack2(p0, p1), tc::add2(tc::pack2(__uint_as_float(dp[4 * q]), __uint_as_float(dp[4 * q + 1])),
-                                                                 tc::pack2(dv.x, dv.y)));
-        const uint64_t db = tc::mul2(tc::pack2(p2, p3), tc::add2(tc::pack2(__uint_as_float(dp[4 * q + 2]), __uint_as_float(dp[4 * q + 3])),
-                                                                 tc::pack2(dv.z, dv.w)));
-        float d0, d1, d2, d3;
-        tc::unpack2(da, d0, d1);
-        tc::unpack2(db, d2, d3);
-        pk[2 * q] = pack_bf16x2(p0, p1);
-        pk[2 * q + 1] = pack_bf16x2(p2, p3);
-        dk[2 * q] = pack_bf16x2(d0, d1);
-        dk[2 * q + 1] = pack_bf16x2(d2, d3);
-      }
-      // in place: this thread's 32 fp32 columns of both buffers are in registers; its bf16 output reuses their first 16
-      tc::tmem_st_x16(tcol + C::kColST, pk);    // P^T  (bf16 pairs): K-slices 2 colhalf, 2 colhalf + 1
-      tc::tmem_st_x16(tcol + C::kColDPT, dk);   // dS^T (bf16 pairs)
-      // dS^T row -> smem (MN-major A operand of dQ = dS K): buffer m&1, 64-query chunk hh, 16-byte pieces 4 colhalf .. +3
-      uint8_t* rowp = sDS + (m & 1) * C::kDsBytes + hh * (128 * 128) + row * 128;
+      for (int c = 0; c < kNC; ++c) {
+        const int ch = C::kAlt ? c : colhalf;  // 32-column half of the sub-tile
+        const uint32_t tcol = lane_addr + st * C::kStageCols + ch * 32;
+        uint32_t s[32], dp[32];
+#if AB_KNOCK & 32
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int piece = colhalf * 4 + q;
-        *reinterpret_cast<uint4*>(rowp + ((piece ^ (row & 7)) << 4)) = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+        for (int q = 0; q < 32; ++q) { s[q] = q * lane; dp[q] = q + lane; }
+#else
+        tc::tmem_ld_x32(tcol + C::kColST, s);
+        tc::tmem_ld_x32(tcol + C::kColDPT, dp);
+        tc::tmem_ld_wait();
+#endif
+        AB_TRACE(6);
+        uint32_t pk[16], dk[16];
+        const float4* l4 = reinterpret_cast<const float4*>(stat + ch * 32);
+        const float4* d4 = reinterpret_cast<const float4*>(stat + 128 + ch * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 lv = l4[q], dv = d4[q];
+          const uint64_t xa = tc::fma2(tc::pack2(__uint_as_float(s[4 * q]), __uint_as_float(s[4 * q + 1])), sc2,
+                                       tc::pack2(lv.x, lv.y));
+          const uint64_t xb = tc::fma2(tc::pack2(__uint_as_float(s[4 * q + 2]), __uint_as_float(s[4 * q + 3])), sc2,
+                                       tc::pack2(lv.z, lv.w));
+          float x0, x1, x2, x3;
+          tc::unpack2(xa, x0, x1);
+          tc::unpack2(xb, x2, x3);
+#if AB_KNOCK & 1
+          const float p0 = x0, p1 = x1, p2 = x2, p3 = x3;
+#else
+          const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1), p2 = tc::fast_exp2(x2), p3 = tc::fast_exp2(x3);
+#endif
+          const uint64_t da = tc::mul2(tc::pack2(p0, p1), tc::add2(tc::pack2(__uint_as_float(dp[4 * q]), __uint_as_float(dp[4 * q + 1])),
+                                                                   tc::pack2(dv.x, dv.y)));
+          const uint64_t db = tc::mul2(tc::pack2(p2, p3), tc::add2(tc::pack2(__uint_as_float(dp[4 * q + 2]), __uint_as_float(dp[4 * q + 3])),
+                                                                   tc::pack2(dv.z, dv.w)));
+          float d0, d1, d2, d3;
+          tc::unpack2(da, d0, d1);
+          tc::unpack2(db, d2, d3);
+          pk[2 * q] = pack_bf16x2(p0, p1);
+          pk[2 * q + 1] = pack_bf16x2(p2, p3);
+          dk[2 * q] = pack_bf16x2(d0, d1);
+          dk[2 * q + 1] = pack_bf16x2(d2, d3);
+        }
+        // in place: this thread's 32 fp32 columns of both buffers are in registers; its bf16 output reuses their first 16
+#if AB_KNOCK & 16
+        if (pk[0] == 0x12345678u && dk[3] == 0x9abcdef0u) tc::tmem_st_x16(tcol + C::kColST, pk);
+#else
+        tc::tmem_st_x16(tcol + C::kColST, pk);    // P^T  (bf16 pairs): K-slices 2 ch, 2 ch + 1
+        tc::tmem_st_x16(tcol + C::kColDPT, dk);   // dS^T (bf16 pairs)
+#endif
+        // dS^T row -> smem (MN-major A operand of dQ = dS K): buffer m&1, 64-query chunk hh, 16-byte pieces 4 ch .. +3
+        uint8_t* rowp = sDS + (m & 1) * C::kDsBytes + hh * (128 * 128) + row * 128;
+#pragma unroll
+        for (int q = 0; q < ((AB_KNOCK & 2) ? 0 : 4); ++q) {
+          const int piece = ch * 4 + q;
+          *reinterpret_cast<uint4*>(rowp + ((piece ^ (row & 7)) << 4)) = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+        }
       }
       AB_TRACE(7);
       tc::tmem_st_wait();
-      tc::fence_proxy_async();  // st.shared (generic proxy) -> tcgen05.mma reads (async proxy)
+      if (!(AB_KNOCK & 1024)) tc::fence_proxy_async();  // st.shared (generic proxy) -> tcgen05.mma reads (async proxy)
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&p_ready[st]);
+      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(&p_ready[st]);
+        tc::mbar_arrive(&ds_ready[m & 1]);
+        if (hh == 0 && i == n_sub - 1) tc::mbar_arrive(&ds_ready[m & 1]);  // odd tail: the tile has no second sub-tile
+      }
       AB_TRACE(8);
-      AB_TRACE(9);
+      AB_TRACEW(1);
     }
 #if OCT_AB_TRACE
     if ((p.dbg & 16) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
       for (int i = 0; i < 8; ++i)
-        for (int k = 0; k < 14; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 16 + k] - g_ab_trace[0]);
+        for (int k = 0; k < 48; ++k) printf("TRACE i%d id%d %lld\n", i + 8, k, g_ab_trace[i * 48 + k] - g_ab_trace[0]);
     }
 #endif
     // epilogue: column half 0 stores dV, half 1 stores dK of this kv tile
@@ -430,12 +494,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   }
 }
 
-// delta[b,h,s] = sum_c dO[b,s,h,c] * O[b,s,h,c]   (one thread per (b,s,h) row: HD bf16 = 64 / 128 contiguous bytes).
+// delta[b,h,s] = sum_c dO[b,s,h,c] * O[b,s,h,c]   (one thread per (b,s,h) row: HD bf16 = 64 / 128 contiguous bytes), stored
+// NEGATED next to -lse * log2(e) in [B,H,Spad] arrays (the form the softmax warps of attn_bwd_tc_kernel consume, fetched per
+// 128-query tile by bulk copies); the rows s in [S, Spad) get -inf / 0 so that padded query columns produce P = dS = 0.
 // The same thread clears the row's slot of the fp32 dQ accumulator (the drain warps of attn_bwd_tc_kernel reduce into it): a
 // separate memset was one more launch per layer (32 per step).  Rows s >= S of the padded accumulator are never read.
 template <int HD>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, float* __restrict__ dq_acc, int64_t total, int S, int H, int Spad) {
+                                  const float* __restrict__ lse, float* __restrict__ nlse2, float* __restrict__ ndelta,
+                                  float* __restrict__ dq_acc, int64_t total, int S, int H, int Spad) {
   pdl_launch_dependents();
   pdl_wait();
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,9 +522,13 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
   const int64_t bs = w / H;
   const int s = (int)(bs % S);
   const int64_t bb = bs / S;
-  delta[(bb * H + hh) * S + s] = acc;
+  const int64_t bh = bb * H + hh;
+  ndelta[bh * Spad + s] = -acc;
+  nlse2[bh * Spad + s] = -lse[bh * S + s] * kLog2e;
+  if (s == S - 1)
+    for (int t = S; t < Spad; ++t) { ndelta[bh * Spad + t] = 0.f; nlse2[bh * Spad + t] = -INFINITY; }
   // accumulator layout per 128-query tile: [row quarter][16-byte chunk][32 rows][4 floats] (see the drain warps)
-  float* tile = dq_acc + ((bb * H + hh) * Spad + (s & ~127)) * HD;
+  float* tile = dq_acc + (bh * Spad + (s & ~127)) * HD;
   const int rr = s & 127;
 #pragma unroll
   for (int c4 = 0; c4 < HD / 4; ++c4)
@@ -500,7 +571,8 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   using C = AbCfg<HD>;
   const int64_t Spad = ceil_div64(S, 128) * 128;
   float* dq_acc = (float*)ws;
-  float* delta = dq_acc + (size_t)B * H * Spad * HD;
+  float* nlse2 = dq_acc + (size_t)B * H * Spad * HD;
+  float* ndelta = nlse2 + (size_t)B * H * Spad;
   CUtensorMap mq, md;
   int rc = make_map4(&mq, qkv, HD, 3 * H, S, B, "oct_attn_bwd(bf16) qkv");
   if (rc) return rc;
@@ -509,7 +581,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   cudaError_t e;
   const int64_t rows = B * S * H;
   oct_launch(attn_delta_kernel<HD>, dim3((unsigned)ceil_div64(rows, 256)), dim3(256), 0, st, 1, (const __nv_bfloat16*)out,
-             (const __nv_bfloat16*)dout, delta, dq_acc, rows, (int)S, (int)H, (int)Spad);
+             (const __nv_bfloat16*)dout, lse, nlse2, ndelta, dq_acc, rows, (int)S, (int)H, (int)Spad);
   rc = oct_check_launch("oct_attn_bwd(bf16,delta)");
   if (rc) return rc;
   static bool attr_done = false;
@@ -520,7 +592,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   }
   AbParams p;
   p.S = (int)S; p.H = (int)H; p.Spad = (int)Spad; p.scale = scale; p.scale_log2e = scale * kLog2e;
-  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dqkv = (__nv_bfloat16*)dqkv;
+  p.nlse2 = nlse2; p.ndelta = ndelta; p.dq_acc = dq_acc; p.dqkv = (__nv_bfloat16*)dqkv;
   { const char* e = getenv("OCT_ATTN_BWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   dim3 grid((unsigned)ceil_div64(S, AB_T), (unsigned)H, (unsigned)B);
   oct_launch(attn_bwd_tc_kernel<HD>, grid, dim3(AB_THREADS), (size_t)C::kSmem, st, 1, mq, md, p);
@@ -536,7 +608,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
 
 size_t oct_attn_bwd_tc_ws_bytes(int64_t B, int64_t S, int64_t H, int64_t d) {
   const int64_t Spad = ceil_div64(S, 128) * 128;
-  return (size_t)B * H * Spad * d * sizeof(float) + (size_t)B * H * S * sizeof(float) + 64;
+  return (size_t)B * H * Spad * d * sizeof(float) + 2 * (size_t)B * H * Spad * sizeof(float) + 64;
 }
 
 int oct_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,

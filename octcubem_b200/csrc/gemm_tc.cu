@@ -121,6 +121,17 @@ struct GemmParams {
 // Protocol: both CTAs' TMA loads complete on the LEADER's full barrier (which the leader arms with the bytes of both);
 // the leader's tcgen05.commit multicasts onto both CTAs' empty / tmem_full barriers; the epilogue warps of both CTAs
 // release an accumulator stage on the leader's tmem_empty barrier (one arrival per warp).
+#ifndef OCT_GEMM_TRACE  // build with -DOCT_GEMM_TRACE=1: clock64 stamps of the phases of a CTA, printed by CTAs 0 / 1 / last
+#define OCT_GEMM_TRACE 0
+#endif
+#if OCT_GEMM_TRACE
+#define G_TRACE(id) do { gtrace[id] = clock64(); } while (0)
+#define G_TRACEW(id) do { if (lane == 0 && w == cta) gtrace[16 + (warp - 2) * 8 + (id)] = clock64(); } while (0)
+#else
+#define G_TRACE(id) do {} while (0)
+#define G_TRACEW(id) do {} while (0)
+#endif
+
 template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair, bool kColsum>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                               const __grid_constant__ CUtensorMap tmap_b,
@@ -129,6 +140,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                                               const GemmParams p) {
   using C = Cfg<BLOCK_N, kColsum, kPair>;
   static_assert(!kColsum || A_MN, "the bias-gradient MMA sums the MN-major A operand over K");
+#if OCT_GEMM_TRACE
+  __shared__ long long gtrace[16 + 8 * 8];
+  if (threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); gtrace[15] = (long long)g; G_TRACE(0); }
+#endif
   pdl_launch_dependents();
   static_assert(!kPair || BLOCK_N == 256 || (BLOCK_N == 128 && !kColsum), "pair mode: 256 x 256 (or 256 x 128) output tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
@@ -185,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (kPair) tc::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) G_TRACE(1);
   pdl_wait();  // everything above overlapped the previous kernel's tail; operands / outputs are touched only below
 
   auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
@@ -246,9 +262,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 tc::tma_load_2d_pair(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], nh + c * 64, k0);
             }
           }
+          if (kb == kb0 && w == cta) G_TRACE(2);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      G_TRACE(3);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -274,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int num_kb = min(num_kb_total, (w / num_tiles + 1) * p.kb_per_split) - (w / num_tiles) * p.kb_per_split;
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(&full_bar[stage], phase);
+          if (kb == 0 && w == cta) G_TRACE(4);
           tc::tcgen05_fence_after();
           const uint32_t a_addr = tc::smem_u32(smem_a + stage * C::kABytes);
           const uint32_t b_addr = tc::smem_u32(smem_b + stage * C::kBBytes);
@@ -298,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         // accumulator complete -> epilogue (pair: of both CTAs)
         if (kPair) tc::mma_commit_pair(&tmem_full[acc], 3); else tc::mma_commit(&tmem_full[acc]);
+        if (w == cta) G_TRACE(5);
       }
       __syncwarp();
       if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -384,6 +404,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
       tc::mbar_wait(&tmem_full[acc], acc_phase);
+      if (w == cta && warp == 2 && lane == 0) G_TRACE(6);
+      G_TRACEW(0);
       tc::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
       if (kColsum && n_blk == 0 && colhalf == 0) {
@@ -405,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tc::tmem_ld_x32(taddr + g * 64, r0);
           tc::tmem_ld_x32(taddr + g * 64 + 32, r1);
           tc::tmem_ld_wait();
+          G_TRACEW(1 + 3 * gg);
           if (gg == kGroups - 1 || nc + 64 >= p.N) release_acc(acc);  // last TMEM read of this tile
           float v[64];
 #pragma unroll
@@ -462,7 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          G_TRACEW(2 + 3 * gg);
           stage_and_store(o, &tmap_d, nc, row0, false);
+          G_TRACEW(3 + 3 * gg);
         }
       } else {
         constexpr int kGroups = BLOCK_N / 64;  // 32-column (128-byte) fp32 groups per column half
@@ -493,18 +518,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       // a tile whose column half lies entirely beyond N never reached an arrive above
       if (n0 + colhalf * (BLOCK_N / 2) >= p.N) release_acc(acc);
+      if (w == cta && warp == 2 && lane == 0) G_TRACE(7);
       if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have left smem and are visible
+    // the staging buffers have been read; global visibility of the stores is the kernel boundary's business (waiting for it
+    // here, `wait_group 0` without .read, kept every CTA ~1.3 us past its last store: clock64 trace)
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (warp == 2 && lane == 0) G_TRACE(8);
   }
 
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (kPair) tc::cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  if (kPair) tc::cluster_sync_all_relaxed();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc::tcgen05_fence_after();
     if (kPair) tc::tmem_dealloc_pair<C::kTmemCols>(tmem_base); else tc::tmem_dealloc<C::kTmemCols>(tmem_base);
   }
+#if OCT_GEMM_TRACE
+  __syncthreads();
+  if (threadIdx.x == 0 && (p.dbg & 2) && (blockIdx.x < 2 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    const long long t0 = gtrace[0];
+    printf("GTRACE cta %d gt0 %lld gt1 %lld | pro %lld tma1 %lld tmaend %lld full1 %lld mmaend %lld epi0 %lld epi1 %lld stored %lld exit %lld\n", (int)blockIdx.x,
+           gtrace[15], (long long)g, gtrace[1] - t0, gtrace[2] - t0, gtrace[3] - t0, gtrace[4] - t0, gtrace[5] - t0, gtrace[6] - t0,
+           gtrace[7] - t0, gtrace[8] - t0, (long long)clock64() - t0);
+    if (blockIdx.x == 0)
+      for (int ww = 0; ww < 8; ++ww)
+        printf("GTRACEW warp %d wake %lld | ld %lld packed %lld staged %lld | ld %lld packed %lld staged %lld\n", ww + 2, gtrace[16 + ww * 8] - t0,
+               gtrace[16 + ww * 8 + 1] - t0, gtrace[16 + ww * 8 + 2] - t0, gtrace[16 + ww * 8 + 3] - t0, gtrace[16 + ww * 8 + 4] - t0,
+               gtrace[16 + ww * 8 + 5] - t0, gtrace[16 + ww * 8 + 6] - t0);
+  }
+#endif
 }
 
 template <bool A_MN, bool B_MN, int BLOCK_N, bool kPair, bool kColsum = false>

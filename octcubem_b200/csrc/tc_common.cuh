@@ -129,8 +129,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Remote arrive with the DEFAULT semantics (release at CTA scope).  `.release.cluster` compiles to a cluster-scope memory
+// barrier that waits for every outstanding write of the SM, the TMA stores in flight included: the GEMM epilogue spent
+// ~2000 clk per tile in it (clock64 trace, profiles/r2_gemm_trace.md).  The hand-offs that use this only order tcgen05
+// traffic, which tcgen05.wait / tcgen05.fence::before_thread_sync already do.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {  // the same warp of BOTH CTAs
@@ -168,11 +172,22 @@ __device__ __forceinline__ void cluster_sync_all() {  // every thread of every C
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous (no memory ordering): "nobody leaves while the peer may still signal this CTA's barriers".
+__device__ __forceinline__ void cluster_sync_all_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// plain (1-D) bulk copy global -> shared, completing on an mbarrier; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
