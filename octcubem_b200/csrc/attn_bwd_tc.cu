@@ -41,6 +41,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef AB_ALT32
 #define AB_ALT32 1
 #endif
+#ifndef AB_POLY   // pairs out of every 4 (two q-iterations) whose exponentials run on the FMA pipe: 0 .. 4
+#define AB_POLY 0
+#endif
+#ifndef AB_MERGE  // 1: warp 9 issues G(i) and S/dP(i + kNS) back to back (warp 11 idle); 0: warp 11 issues S/dP after g_done
+#define AB_MERGE 1
+#endif
 #ifndef AB_KNOCK  // timing experiments ONLY (results are wrong): 1 no exponentials, 2 no dS^T st.shared, 4 no dQ MMAs, 8 no G MMAs,
 #define AB_KNOCK 0  // 16 no tcgen05.st of P^T / dS^T, 32 no tcgen05.ld of the scores, 64 no S/dP MMAs
 #endif
@@ -229,11 +235,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       constexpr uint32_t idesc_acc = tc::make_idesc(tc::kFmtBF16, false, true, 128, HD);       // P^T dO_h, dS^T Q_h (TS)
       const uint64_t dQ0_mn = tc::make_smem_desc(tc::smem_u32(sQ), C::kTileBytes, C::kSBO, C::kSwz);
       const uint64_t dDO0_mn = tc::make_smem_desc(tc::smem_u32(sDO), C::kTileBytes, C::kSBO, C::kSwz);
+#if AB_MERGE
+      // AB_MERGE: this warp also queues S/dP(i + kNS) right behind G(i) (same stage; the in-order MMA stream of one thread
+      // needs no completion wait in between: one commit -> barrier -> wake hop (~500 clk) less per stage round trip)
+      constexpr uint32_t idesc_st = tc::make_idesc(tc::kFmtBF16, false, false, 128, AB_SUB);
+      const uint64_t dK_kmaj = tc::make_smem_desc(tc::smem_u32(sK), 16, C::kSBO, C::kSwz);
+      const uint64_t dV_kmaj = tc::make_smem_desc(tc::smem_u32(sV), 16, C::kSBO, C::kSwz);
+      const uint64_t dQ0_kmaj = tc::make_smem_desc(tc::smem_u32(sQ), 16, C::kSBO, C::kSwz);
+      const uint64_t dDO0_kmaj = tc::make_smem_desc(tc::smem_u32(sDO), 16, C::kSBO, C::kSwz);
+      auto issue_sdp = [&](int j) {  // elected lane
+        const uint32_t joff = ((j >> 1) % C::kQStages) * kStageStep + (j & 1) * kHalfStep;
+        const uint32_t jcol = tmem_base + (j % C::kNS) * C::kStageCols;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          tc::mma_ss(jcol + C::kColST, dK_kmaj + k * kKStepK, dQ0_kmaj + joff + k * kKStepK, idesc_st, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          tc::mma_ss(jcol + C::kColDPT, dV_kmaj + k * kKStepK, dDO0_kmaj + joff + k * kKStepK, idesc_st, k != 0);
+        tc::mma_commit(&sdp_full[j % C::kNS]);
+      };
+      auto wait_for_sdp = [&](int j) {  // all lanes: operands of S/dP(j) present, dS^T buffer of its query tile released
+        if ((j & 1) == 0) {
+          const int t = j >> 1;
+          tc::mbar_wait(&q_full[t % C::kQStages], (t / C::kQStages) & 1);
+          if (t >= 2) tc::mbar_wait(&ds_free[t & 1], ((t - 2) >> 1) & 1);
+        }
+      };
+      tc::mbar_wait(kv_full, 0);
+      for (int j = 0; j < C::kNS && j < n_sub; ++j) {
+        wait_for_sdp(j);
+        tc::tcgen05_fence_after();
+        if (tc::elect_one()) issue_sdp(j);
+        __syncwarp();
+      }
+#endif
       for (int i = 0; i < n_sub; ++i) {
         const int m = i >> 1, hh = i & 1, st = i % C::kNS;
         const uint32_t off = (m % C::kQStages) * kStageStep + hh * kHalfStep;
         const uint32_t tcol = tmem_base + st * C::kStageCols;
         AB_TRACE(0);
+#if AB_MERGE
+        if (i + C::kNS < n_sub) wait_for_sdp(i + C::kNS);  // long satisfied; off the p_ready -> G critical path
+#endif
         AB_WAIT(&p_ready[st], (i / C::kNS) & 1);  // bf16 P^T / dS^T of sub-tile i in TMEM
         tc::tcgen05_fence_after();
         AB_TRACE(1);
@@ -246,9 +289,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           for (int k = 0; k < ((AB_KNOCK & 8) ? 0 : AB_SUB / 16); ++k)  // dK += dS^T Q_h
             tc::mma_ts(tmem_base + C::kColDK, tcol + C::kColDPT + C::slice_off(k), dQ0_mn + off + k * kKStepMN, idesc_acc,
                        (i | k) != 0);
+#if !AB_MERGE
           tc::mma_commit(&g_done[st]);
+#endif
           // Q_m / dO_m fully consumed: this G is causally after S/dP of both halves (p_ready <- softmax <- sdp_full)
           if (hh == 1 || i == n_sub - 1) tc::mma_commit(&q_empty[m % C::kQStages]);
+#if AB_MERGE
+          if (i + C::kNS < n_sub) issue_sdp(i + C::kNS);
+#endif
         }
         __syncwarp();
         AB_TRACE(3);
@@ -277,7 +325,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         __syncwarp();
         AB_TRACE(13);
       }
-    } else {
+    } else if (!AB_MERGE) {
       constexpr uint32_t idesc_st = tc::make_idesc(tc::kFmtBF16, false, false, 128, AB_SUB);  // K Q_h^T, V dO_h^T
       const uint64_t dK_kmaj = tc::make_smem_desc(tc::smem_u32(sK), 16, C::kSBO, C::kSwz);       // K as K-major A
       const uint64_t dV_kmaj = tc::make_smem_desc(tc::smem_u32(sV), 16, C::kSBO, C::kSwz);       // V as K-major A
@@ -381,29 +429,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       // needed: query columns past S carry lse = +inf (P = 0), and kv rows past S have zero-filled K / V rows, so
       // their (finite) P and dS only reach dV / dK rows that are never stored and add dS * 0 to dQ.
       const uint64_t sc2 = tc::pack2(p.scale_log2e, p.scale_log2e);
-#pragma unroll
-      for (int c = 0; c < kNC; ++c) {
-        const int ch = C::kAlt ? c : colhalf;  // 32-column half of the sub-tile
-        const uint32_t tcol = lane_addr + st * C::kStageCols + ch * 32;
-        uint32_t s[32], dp[32];
+      // 16-query chunks (= one K-slice of the gradient MMAs each), software-pipelined: the TMEM loads of chunk k + 1 are in
+      // flight while chunk k is computed, so only the first load of a sub-tile is exposed (tcgen05.wait::ld covers every
+      // outstanding load: wait, THEN issue the next pair).  kAlt: chunks 0-3; column-split form: chunks 2 colhalf, 2 colhalf + 1.
+      constexpr int kChunks = C::kAlt ? 4 : 2;
+      const int k0 = C::kAlt ? 0 : 2 * colhalf;
+      const uint32_t tst = lane_addr + st * C::kStageCols;
+      uint8_t* rowp = sDS + (m & 1) * C::kDsBytes + hh * (128 * 128) + row * 128;
+      uint32_t s[2][16], dp[2][16];
 #if AB_KNOCK & 32
 #pragma unroll
-        for (int q = 0; q < 32; ++q) { s[q] = q * lane; dp[q] = q + lane; }
+      for (int q = 0; q < 16; ++q) { s[0][q] = s[1][q] = q * lane; dp[0][q] = dp[1][q] = q + lane; }
 #else
-        tc::tmem_ld_x32(tcol + C::kColST, s);
-        tc::tmem_ld_x32(tcol + C::kColDPT, dp);
-        tc::tmem_ld_wait();
+      tc::tmem_ld_x16(tst + C::kColST + k0 * 16, s[0]);
+      tc::tmem_ld_x16(tst + C::kColDPT + k0 * 16, dp[0]);
+      tc::tmem_ld_wait();
 #endif
-        AB_TRACE(6);
-        uint32_t pk[16], dk[16];
-        const float4* l4 = reinterpret_cast<const float4*>(stat + ch * 32);
-        const float4* d4 = reinterpret_cast<const float4*>(stat + 128 + ch * 32);
+      AB_TRACE(6);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+      for (int kk = 0; kk < kChunks; ++kk) {
+        const int k = k0 + kk;  // chunk = K-slice index inside the 64-query sub-tile
+        uint32_t(&sc)[16] = s[kk & 1];
+        uint32_t(&dc)[16] = dp[kk & 1];
+#if !(AB_KNOCK & 32)
+        if (kk + 1 < kChunks) {
+          tc::tmem_ld_x16(tst + C::kColST + (k + 1) * 16, s[(kk + 1) & 1]);
+          tc::tmem_ld_x16(tst + C::kColDPT + (k + 1) * 16, dp[(kk + 1) & 1]);
+        }
+#endif
+        uint32_t pk[8], dk[8];
+        const float4* l4 = reinterpret_cast<const float4*>(stat + k * 16);
+        const float4* d4 = reinterpret_cast<const float4*>(stat + 128 + k * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
           const float4 lv = l4[q], dv = d4[q];
-          const uint64_t xa = tc::fma2(tc::pack2(__uint_as_float(s[4 * q]), __uint_as_float(s[4 * q + 1])), sc2,
+          const uint64_t xa = tc::fma2(tc::pack2(__uint_as_float(sc[4 * q]), __uint_as_float(sc[4 * q + 1])), sc2,
                                        tc::pack2(lv.x, lv.y));
-          const uint64_t xb = tc::fma2(tc::pack2(__uint_as_float(s[4 * q + 2]), __uint_as_float(s[4 * q + 3])), sc2,
+          const uint64_t xb = tc::fma2(tc::pack2(__uint_as_float(sc[4 * q + 2]), __uint_as_float(sc[4 * q + 3])), sc2,
                                        tc::pack2(lv.z, lv.w));
           float x0, x1, x2, x3;
           tc::unpack2(xa, x0, x1);
@@ -411,11 +473,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 #if AB_KNOCK & 1
           const float p0 = x0, p1 = x1, p2 = x2, p3 = x3;
 #else
-          const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1), p2 = tc::fast_exp2(x2), p3 = tc::fast_exp2(x3);
+          // AB_POLY of every 4 pairs go through the FMA-pipe polynomial (tc::exp2_poly2, 7.6e-5 relative: 25x below the
+          // bf16 rounding P receives) instead of the MUFU: a softmax warp alone on its scheduler is bound by the 8 clk per
+          // MUFU.EX2 warp instruction, with the FMA pipe ~75 % idle
+          float p0, p1, p2, p3;
+          const bool a_poly = (AB_POLY == 4) || (AB_POLY == 3 && (q & 1));
+          const bool b_poly = (AB_POLY >= 2) || (AB_POLY == 1 && (q & 1));
+          if (a_poly) tc::exp2_poly2(xa, p0, p1); else { p0 = tc::fast_exp2(x0); p1 = tc::fast_exp2(x1); }
+          if (b_poly) tc::exp2_poly2(xb, p2, p3); else { p2 = tc::fast_exp2(x2); p3 = tc::fast_exp2(x3); }
 #endif
-          const uint64_t da = tc::mul2(tc::pack2(p0, p1), tc::add2(tc::pack2(__uint_as_float(dp[4 * q]), __uint_as_float(dp[4 * q + 1])),
+          const uint64_t da = tc::mul2(tc::pack2(p0, p1), tc::add2(tc::pack2(__uint_as_float(dc[4 * q]), __uint_as_float(dc[4 * q + 1])),
                                                                    tc::pack2(dv.x, dv.y)));
-          const uint64_t db = tc::mul2(tc::pack2(p2, p3), tc::add2(tc::pack2(__uint_as_float(dp[4 * q + 2]), __uint_as_float(dp[4 * q + 3])),
+          const uint64_t db = tc::mul2(tc::pack2(p2, p3), tc::add2(tc::pack2(__uint_as_float(dc[4 * q + 2]), __uint_as_float(dc[4 * q + 3])),
                                                                    tc::pack2(dv.z, dv.w)));
           float d0, d1, d2, d3;
           tc::unpack2(da, d0, d1);
@@ -425,20 +494,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           dk[2 * q] = pack_bf16x2(d0, d1);
           dk[2 * q + 1] = pack_bf16x2(d2, d3);
         }
-        // in place: this thread's 32 fp32 columns of both buffers are in registers; its bf16 output reuses their first 16
+        // in place: the bf16 K-slice k goes over fp32 columns this thread has already consumed (slice_off(k) <= 16 k)
 #if AB_KNOCK & 16
-        if (pk[0] == 0x12345678u && dk[3] == 0x9abcdef0u) tc::tmem_st_x16(tcol + C::kColST, pk);
+        if (pk[0] == 0x12345678u && dk[3] == 0x9abcdef0u) tc::tmem_st_x8(tst + C::kColST + C::slice_off(k), pk);
 #else
-        tc::tmem_st_x16(tcol + C::kColST, pk);    // P^T  (bf16 pairs): K-slices 2 ch, 2 ch + 1
-        tc::tmem_st_x16(tcol + C::kColDPT, dk);   // dS^T (bf16 pairs)
+        tc::tmem_st_x8(tst + C::kColST + C::slice_off(k), pk);    // P^T  (bf16 pairs)
+        tc::tmem_st_x8(tst + C::kColDPT + C::slice_off(k), dk);   // dS^T (bf16 pairs)
 #endif
-        // dS^T row -> smem (MN-major A operand of dQ = dS K): buffer m&1, 64-query chunk hh, 16-byte pieces 4 ch .. +3
-        uint8_t* rowp = sDS + (m & 1) * C::kDsBytes + hh * (128 * 128) + row * 128;
+        // dS^T row -> smem (MN-major A operand of dQ = dS K): buffer m&1, 64-query chunk hh, 16-byte pieces 2 k, 2 k + 1
 #pragma unroll
-        for (int q = 0; q < ((AB_KNOCK & 2) ? 0 : 4); ++q) {
-          const int piece = ch * 4 + q;
+        for (int q = 0; q < ((AB_KNOCK & 2) ? 0 : 2); ++q) {
+          const int piece = k * 2 + q;
           *reinterpret_cast<uint4*>(rowp + ((piece ^ (row & 7)) << 4)) = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
         }
+#if !(AB_KNOCK & 32)
+        if (kk + 1 < kChunks) tc::tmem_ld_wait();
+#endif
       }
       AB_TRACE(7);
       tc::tmem_st_wait();

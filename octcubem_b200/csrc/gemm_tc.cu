@@ -611,11 +611,13 @@ int oct_gemm_tc_bf16(int layout, const void* A, const void* B, void* D, int d_dt
   CUtensorMap ta, tb;
   int rc = make_operand_map(&ta, A, a_mn, M, K, lda, BLOCK_M, "oct_gemm(bf16) A");
   if (rc) return rc;
-  // pair mode (2-CTA clusters running cta_group::2 MMAs on 256 x 256 tiles) whenever there are at least two m-blocks
-  // ... and the contraction is long enough for the main loop to matter: at K <= 512 (8 k-blocks per tile) the tile time is
-  // the epilogue's, and the pair's cross-CTA accumulator hand-off only adds latency (tools/time_gemm_shapes.py)
+  // pair mode (2-CTA clusters running cta_group::2 MMAs on 256 x 256 tiles) whenever there are at least two m-blocks.
+  // At K <= 512 (8 k-blocks per tile) the tile time is the epilogue's: the GELU / dGELU epilogues are slower in pair mode
+  // (93 -> 97 us at the decoder fc1), the plain and bias ones faster since the remote accumulator release stopped
+  // costing a cluster-scope fence (dec Wqkv 56.1 -> 49.2 us, out_proj 29.4 -> 26.6 us; tools/time_gemm_shapes.py)
   static const int pair_min_k = [] { const char* e = getenv("OCT_GEMM_PAIR_MIN_K"); return e ? atoi(e) : 512; }();
-  const bool pair = (M > BLOCK_M) && (block_n == 256 || (block_n == 128 && !colsum)) && K > pair_min_k &&
+  const bool light_epilogue = (epilogue == OCT_EPI_NONE || epilogue == OCT_EPI_BIAS) && d_dtype == OCT_BF16;
+  const bool pair = (M > BLOCK_M) && (block_n == 256 || (block_n == 128 && !colsum)) && (K > pair_min_k || light_epilogue) &&
                     (getenv("OCT_GEMM_NO_PAIR") == nullptr);
   rc = make_operand_map(&tb, B, b_mn, N, K, ldb, pair ? block_n / 2 : block_n, "oct_gemm(bf16) B");
   if (rc) return rc;
