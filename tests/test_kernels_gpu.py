@@ -415,6 +415,46 @@ def test_gemm(layout, compute, M, N, K):
     assert rel(out, a.double() @ b.double().t()) < (2e-6 if K <= 8192 else 2e-5)  # fp32 accumulation over K
 
 
+@pytest.mark.parametrize("layout,M,N,K,epi", [(GEMM_NT, 3280, 1024, 1024, "bias"), (GEMM_NT, 3280, 3072, 1024, "bias"),
+                                              (GEMM_NN, 3280, 1024, 4096, "none"), (GEMM_NN, 3280, 1024, 3072, "none"),
+                                              (GEMM_NT, 3280, 4096, 1024, "gelu"), (GEMM_NN, 3280, 4096, 1024, "dgelu"),
+                                              (GEMM_NT, 3000, 1000, 576, "bias"), (GEMM_NT, 32776, 1536, 512, "bias"),
+                                              (GEMM_NN, 32776, 512, 512, "none"), (GEMM_NT, 3280, 2064, 1024, "gelu")])
+def test_gemm_bf16_out_step_shapes(layout, M, N, K, epi):
+    """bf16-output GEMMs at the step's shapes (pair and single-CTA tiles, ragged M / N tails) with every fused epilogue,
+    against fp64."""
+    from octcubem_b200._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(N, K, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, generator=g)
+    pre = torch.randn(M, N, generator=g).bfloat16()
+    Bm = b.to(DEV) if layout == GEMM_NT else b.t().contiguous().to(DEV)
+    acc = a.double() @ b.double().t()
+    code = {"none": EPI_NONE, "bias": EPI_BIAS, "gelu": EPI_BIAS_GELU, "dgelu": EPI_DGELU}[epi]
+    aux = None
+    if epi == "gelu":
+        aux = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    elif epi == "dgelu":
+        aux = pre.to(DEV)
+    out = ops.gemm(layout, a.to(DEV), Bm, M, N, K, torch.bfloat16, code, bias=bias.to(DEV) if epi in ("bias", "gelu") else None,
+                   aux=aux, compute=OCT_BF16)
+    if epi == "none":
+        want = acc
+    elif epi == "bias":
+        want = acc + bias.double()
+    elif epi == "gelu":
+        z = (acc + bias.double()).to(torch.bfloat16)          # GELU of the bf16-rounded pre-activation (SURVEY Q9)
+        assert rel(aux, acc + bias.double()) < 4e-3
+        want = F.gelu(z.double())
+    else:
+        x = pre.double().requires_grad_(True)
+        F.gelu(x).backward(acc)
+        want = x.grad
+    assert rel(out, want) < 4e-3
+    assert torch.isfinite(out.float()).all()
+
+
 @pytest.mark.parametrize("n_out,k_in,tokens", [(3072, 1024, 3280), (1024, 1024, 3280), (1536, 512, 32776), (512, 2048, 4104),
                                                (768, 512, 8200), (200, 136, 72), (128, 128, 2000), (1024, 768, 3272)])
 def test_wgrad_bias_fused(n_out, k_in, tokens):
