@@ -367,43 +367,49 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& p0, float& p1) {
   p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
 }
 
-// ---- GELU / dGELU of a PAIR on packed fp32x2 math (same A&S 7.1.26 erfc as gelu_fast in common.cuh, same constants) ----
-// The K = 512 GEMMs of the decoder MLP are bound by their epilogue (ncu: tensor pipe 30-35 % busy at fc1+GELU / fc2-dgrad+dGELU,
-// profiles/r1_gemm_ncu.md): ~30 scalar instructions per pair of outputs become 18-22.
+// ---- GELU / dGELU of a PAIR for the bf16 GEMM epilogues (packed fp32x2 math, ONE MUFU per element) ----
+// The K = 512 GEMMs of the decoder MLP are bound by their epilogue: per 128 x 256 tile the A&S 7.1.26 erfc form cost
+// ~14 instructions and 2 MUFU (rcp + ex2) per element = ~4300 issue clk and 4096 MUFU clk against 4096 clk of MMAs
+// (profiles/r2_gemm_trace.md).  Phi(x) = 1/2 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with a least-squares / minimax fit of the
+// odd polynomial: |x Phi(x) - gelu(x)| <= 3.0e-5 and |d/dx - gelu'(x)| <= 1.2e-4 over all x (exact tanh); tanh.approx.f32
+// adds <= 2^-11 relative on tanh, i.e. <= 2.5e-4 |x| on the output — an order of magnitude below the bf16 rounding
+// (2^-9 relative) the result receives.  x^2 is clamped at 36 inside the polynomial (c2 < 0; tanh has saturated by then).
+// The fp32 mode keeps the 1.5e-7 erfc form (common.cuh gelu_fast).
 __device__ __forceinline__ uint64_t bcast2(float c) { return pack2(c, c); }
-__device__ __forceinline__ void gelu_parts2(float x0, float x1, uint64_t& nax, uint64_t& tail, uint64_t& e) {
-  nax = pack2(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));  // -|x|
-  const uint64_t u = fma2(nax, bcast2(-0.3275911f * 0.70710678118654752440f), bcast2(1.f));
-  float u0, u1, t0, t1;
-  unpack2(u, u0, u1);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
-  const uint64_t t = pack2(t0, t1);
-  uint64_t poly = fma2(bcast2(0.5f * 1.061405429f), t, bcast2(0.5f * -1.453152027f));
-  poly = fma2(poly, t, bcast2(0.5f * 1.421413741f));
-  poly = fma2(poly, t, bcast2(0.5f * -0.284496736f));
-  poly = fma2(poly, t, bcast2(0.5f * 0.254829592f));
-  poly = mul2(poly, t);
-  const uint64_t x = pack2(x0, x1);
-  float a0, a1;
-  unpack2(mul2(mul2(x, x), bcast2(-0.72134752044448170368f)), a0, a1);  // -x^2/2 in log2 units
-  e = pack2(fast_exp2(a0), fast_exp2(a1));
-  tail = mul2(poly, e);  // Phi(-|x|)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kGeluC0 = 7.97458471e-01f, kGeluC1 = 3.70503451e-02f, kGeluC2 = -3.58732362e-04f;
+// -> t = tanh(u(x)) for the pair and s = min(x^2, 36)
+__device__ __forceinline__ void gelu_tanh2(uint64_t x, uint64_t& t, uint64_t& s) {
+  float s0, s1;
+  unpack2(mul2(x, x), s0, s1);
+  s = pack2(fminf(s0, 36.f), fminf(s1, 36.f));
+  uint64_t poly = fma2(bcast2(kGeluC2), s, bcast2(kGeluC1));
+  poly = fma2(poly, s, bcast2(kGeluC0));
+  float u0, u1;
+  unpack2(mul2(poly, x), u0, u1);
+  t = pack2(tanh_approx(u0), tanh_approx(u1));
 }
 __device__ __forceinline__ void gelu_fast2(float x0, float x1, float& y0, float& y1) {
-  uint64_t nax, tail, e;
-  gelu_parts2(x0, x1, nax, tail, e);
-  unpack2(fma2(nax, tail, pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), y0, y1);  // relu(x) - |x| Phi(-|x|) = x Phi(x)
+  const uint64_t x = pack2(x0, x1);
+  uint64_t t, s;
+  gelu_tanh2(x, t, s);
+  unpack2(mul2(x, fma2(t, bcast2(0.5f), bcast2(0.5f))), y0, y1);  // x Phi(x)
 }
-// dy * gelu'(x) for a pair: gelu'(x) = Phi(x) + x phi(x), Phi(x) = 1/2 + copysign(1/2 - Phi(-|x|), x)
+// dy * d/dx [x Phi(x)] for a pair: Phi + x/2 (1 - t^2) u'(x), u' = c0 + 3 c1 s + 5 c2 s^2 (the derivative of the SAME
+// approximation the forward evaluates; where s is clamped 1 - t^2 is 0 in fp32)
 __device__ __forceinline__ void gelu_fast_grad2(float x0, float x1, float dy0, float dy1, float& g0, float& g1) {
-  uint64_t nax, tail, e;
-  gelu_parts2(x0, x1, nax, tail, e);
-  float h0, h1;
-  unpack2(fma2(tail, bcast2(-1.f), bcast2(0.5f)), h0, h1);  // 1/2 - tail >= 0
-  const uint64_t cdf = add2(bcast2(0.5f), pack2(__uint_as_float(__float_as_uint(h0) | (__float_as_uint(x0) & 0x80000000u)),
-                                               __uint_as_float(__float_as_uint(h1) | (__float_as_uint(x1) & 0x80000000u))));
-  const uint64_t d = fma2(mul2(pack2(x0, x1), bcast2(0.39894228040143267794f)), e, cdf);
+  const uint64_t x = pack2(x0, x1);
+  uint64_t t, s;
+  gelu_tanh2(x, t, s);
+  uint64_t du = fma2(bcast2(2.5f * kGeluC2), s, bcast2(1.5f * kGeluC1));
+  du = fma2(du, s, bcast2(0.5f * kGeluC0));                          // u'(x) / 2
+  const uint64_t om = fma2(t, mul2(t, bcast2(-1.f)), bcast2(1.f));   // 1 - t^2
+  const uint64_t phi = fma2(t, bcast2(0.5f), bcast2(0.5f));
+  const uint64_t d = fma2(mul2(x, du), om, phi);
   unpack2(mul2(d, pack2(dy0, dy1)), g0, g1);
 }
 
