@@ -64,7 +64,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {  // try_wait itself blocks for a HW-defined slice; this is many seconds
+    if (++spins > (1u << 22)) {  // try_wait itself blocks for a HW-defined slice (~4 us): ~17 s
       printf("octcube_b200: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
