@@ -576,10 +576,24 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
                                   float* __restrict__ dq_acc, int64_t total, int S, int H, int Spad) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per (b, h, s) with s FASTEST (over the padded length): the statistics and the accumulator slots of a warp are
+  // contiguous; the HD-element rows it reads are H * HD elements apart but each is a whole number of sectors.  (With h fastest
+  // — the first version of this kernel — every warp touched 32 different lines per statistics access and scattered 16-byte
+  // zeroing stores over 32 accumulator tiles: 40 us instead of 15 us at the decoder shape.)
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (bb * H + hh) * Spad + s
   if (w >= total) return;
-  const uint4* a = reinterpret_cast<const uint4*>(out + w * HD);
-  const uint4* d = reinterpret_cast<const uint4*>(dout + w * HD);
+  const int s = (int)(w % Spad);
+  const int64_t bh = w / Spad;
+  if (s >= S) {  // padded query rows: P = dS = 0
+    ndelta[w] = 0.f;
+    nlse2[w] = -INFINITY;
+    return;
+  }
+  const int hh = (int)(bh % H);
+  const int64_t bb = bh / H;
+  const int64_t row = ((bb * S + s) * H + hh) * HD;
+  const uint4* a = reinterpret_cast<const uint4*>(out + row);
+  const uint4* d = reinterpret_cast<const uint4*>(dout + row);
   float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) {
@@ -589,15 +603,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
     acc += (x0.x * y0.x + x0.y * y0.y) + (x1.x * y1.x + x1.y * y1.y) + (x2.x * y2.x + x2.y * y2.y) +
            (x3.x * y3.x + x3.y * y3.y);
   }
-  const int hh = (int)(w % H);
-  const int64_t bs = w / H;
-  const int s = (int)(bs % S);
-  const int64_t bb = bs / S;
-  const int64_t bh = bb * H + hh;
-  ndelta[bh * Spad + s] = -acc;
-  nlse2[bh * Spad + s] = -lse[bh * S + s] * kLog2e;
-  if (s == S - 1)
-    for (int t = S; t < Spad; ++t) { ndelta[bh * Spad + t] = 0.f; nlse2[bh * Spad + t] = -INFINITY; }
+  ndelta[w] = -acc;
+  nlse2[w] = -lse[bh * S + s] * kLog2e;
   // accumulator layout per 128-query tile: [row quarter][16-byte chunk][32 rows][4 floats] (see the drain warps)
   float* tile = dq_acc + (bh * Spad + (s & ~127)) * HD;
   const int rr = s & 127;
@@ -606,26 +613,40 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
     *reinterpret_cast<float4*>(tile + (((rr >> 5) * (HD / 4) + c4) * 32 + (rr & 31)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// dq (bf16, into dqkv[:, :, 0]) = scale * dq_acc
+// dq (bf16, into dqkv[:, :, 0]) = scale * dq_acc.  One block per 128-query tile of one (batch, head): the accumulator tile
+// ([row quarter][16-byte chunk][32 rows][4 floats], see the drain warps of attn_bwd_tc_kernel) is read contiguously, transposed
+// through shared memory, and written as whole HD-element rows (with one thread per 16-byte piece of the OUTPUT every read
+// was a half-used sector 512 bytes from the next one).
 template <int HD>
-__global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, int S, int H,
-                                       int Spad, float scale, int64_t total4) {
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
+                                                              int S, int H, int Spad, float scale) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*S*H*HD/4
-  if (i >= total4) return;
-  const int c4 = (int)(i % (HD / 4));
-  int64_t r = i / (HD / 4);
-  const int hh = (int)(r % H); r /= H;
-  const int s = (int)(r % S);
-  const int64_t bb = r / S;
-  // accumulator layout per 128-query tile: [row quarter][16-byte chunk][32 rows][4 floats] (see the drain warps of
-  // attn_bwd_tc_kernel)
-  const int rr = s & 127;
-  const float4 v = *reinterpret_cast<const float4*>(dq_acc + ((bb * H + hh) * Spad + (s & ~127)) * HD +
-                                                    (((rr >> 5) * (HD / 4) + c4) * 32 + (rr & 31)) * 4);
-  __nv_bfloat16* dst = dqkv + (((bb * S + s) * 3 + 0) * H + hh) * HD + c4 * 4;
-  Vec4<__nv_bfloat16>::st(dst, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
+  constexpr int kPitch = HD + 4;  // floats per staged row: float4 stores of a quarter-warp land in 32 distinct banks
+  __shared__ float tile[128 * kPitch];
+  const int mt = blockIdx.x;
+  const int64_t bh = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(dq_acc + (bh * Spad + (int64_t)mt * 128) * HD);
+  for (int i = threadIdx.x; i < 128 * HD / 4; i += 256) {
+    const int r = i & 31, c4 = (i >> 5) % (HD / 4), q = i / (32 * (HD / 4));
+    *reinterpret_cast<float4*>(&tile[(q * 32 + r) * kPitch + c4 * 4]) = src[i];
+  }
+  __syncthreads();
+  const int hh = (int)(bh % H);
+  const int64_t bb = bh / H;
+  for (int j = threadIdx.x; j < 128 * HD / 8; j += 256) {
+    const int row = j / (HD / 8), c8 = j % (HD / 8);
+    const int s = mt * 128 + row;
+    if (s >= S) continue;
+    const float4 v0 = *reinterpret_cast<const float4*>(&tile[row * kPitch + c8 * 8]);
+    const float4 v1 = *reinterpret_cast<const float4*>(&tile[row * kPitch + c8 * 8 + 4]);
+    uint4 o;
+    o.x = pack_bf16x2(v0.x * scale, v0.y * scale);
+    o.y = pack_bf16x2(v0.z * scale, v0.w * scale);
+    o.z = pack_bf16x2(v1.x * scale, v1.y * scale);
+    o.w = pack_bf16x2(v1.z * scale, v1.w * scale);
+    *reinterpret_cast<uint4*>(dqkv + (((bb * S + s) * 3 + 0) * H + hh) * HD + c8 * 8) = o;
+  }
 }
 
 int make_map4(CUtensorMap* map, const void* base, int64_t d, int64_t hdim, int64_t S, int64_t B, const char* who) {
@@ -650,7 +671,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   rc = make_map4(&md, dout, HD, H, S, B, "oct_attn_bwd(bf16) dout");
   if (rc) return rc;
   cudaError_t e;
-  const int64_t rows = B * S * H;
+  const int64_t rows = B * H * Spad;
   oct_launch(attn_delta_kernel<HD>, dim3((unsigned)ceil_div64(rows, 256)), dim3(256), 0, st, 1, (const __nv_bfloat16*)out,
              (const __nv_bfloat16*)dout, lse, nlse2, ndelta, dq_acc, rows, (int)S, (int)H, (int)Spad);
   rc = oct_check_launch("oct_attn_bwd(bf16,delta)");
@@ -669,9 +690,8 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   oct_launch(attn_bwd_tc_kernel<HD>, grid, dim3(AB_THREADS), (size_t)C::kSmem, st, 1, mq, md, p);
   rc = oct_check_launch("oct_attn_bwd(bf16)");
   if (rc) return rc;
-  const int64_t total4 = B * S * H * (HD / 4);
-  oct_launch(attn_dq_convert_kernel<HD>, dim3((unsigned)ceil_div64(total4, 256)), dim3(256), 0, st, 1, (const float*)dq_acc,
-             (__nv_bfloat16*)dqkv, (int)S, (int)H, (int)Spad, scale, total4);
+  oct_launch(attn_dq_convert_kernel<HD>, dim3((unsigned)(Spad / 128), (unsigned)(B * H)), dim3(256), 0, st, 1, (const float*)dq_acc,
+             (__nv_bfloat16*)dqkv, (int)S, (int)H, (int)Spad, scale);
   return oct_check_launch("oct_attn_bwd(bf16,dq)");
 }
 
