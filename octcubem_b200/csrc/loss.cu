@@ -62,17 +62,24 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
   const int t = j / G, s = j - t * G, h = s / wp, w = s - h * wp;
   const TP* prow = pred + ((size_t)b * pred_rows + pred_row0 + j) * P;
 
+  // The recipe's patch (3 x 16 x 16 = 768 pixels) is exactly one float4 per thread: it is fetched ONCE and kept in registers
+  // across the mean / variance / error passes (three dependent trips to L1 per token before).
+  const bool single = (P4 <= kLossThreads);
+  float4 tg0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (single && (int)threadIdx.x < P4) tg0 = load_target4(imgs, frame_idx, b, t, h, w, threadIdx.x, T, H, W, p, u, cl);
+  auto target = [&](int e4) { return single ? tg0 : load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl); };
+
   float mean = 0.f, inv_std = 1.f;
   if (norm_pix) {  // models:644-647 — mean, UNBIASED variance, eps 1e-6
     float sum = 0.f;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 v = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
+      float4 v = target(e4);
       sum += (v.x + v.y) + (v.z + v.w);
     }
     mean = block_sum(sum, sred) / (float)P;
     float sq = 0.f;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 v = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
+      float4 v = target(e4);
       const float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
       sq += (a * a + c * c) + (d * d + e * e);
     }
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
   if (!kBackward) {
     float acc = 0.f;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 tg = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
+      float4 tg = target(e4);
       const float4 pr = Vec4<TP>::ld(prow + e4 * 4);
       const float a = pr.x - (tg.x - mean) * inv_std, c = pr.y - (tg.y - mean) * inv_std;
       const float d = pr.z - (tg.z - mean) * inv_std, e = pr.w - (tg.w - mean) * inv_std;
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_token_kernel(
     const float coef = dloss[0] * 2.f / ((float)P * mask_sum[0]);
     TD* drow = dpred + ((size_t)b * pred_rows + pred_row0 + j) * P;
     for (int e4 = threadIdx.x; e4 < P4; e4 += kLossThreads) {
-      float4 tg = load_target4(imgs, frame_idx, b, t, h, w, e4, T, H, W, p, u, cl);
+      float4 tg = target(e4);
       const float4 pr = Vec4<TP>::ld(prow + e4 * 4);
       float4 o;
       o.x = coef * (pr.x - (tg.x - mean) * inv_std);

@@ -270,16 +270,25 @@ __global__ void gather_tokens_bwd_pos_kernel(const float* __restrict__ dout, con
       s_sorted[r] = v;
     }
     __syncthreads();
-    for (int i = 0; i < n; ++i) {
-      const int f = s_sorted[i];
-      const int b = f / keep, r = f - b * keep;
-      const float* src = dout + ((size_t)b * rows + r + has_cls) * C;
+    // rows are ADDED in list order (reproducible), but fetched eight at a time: a temporal slot collects ~B*keep/Tp rows
+    // (204 at the bench shape), and one dependent L2 round trip per row made the 16 temporal CTAs the whole kernel (92 us)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = (threadIdx.x + k * blockDim.x) * 4;
-        if (c < C) {
-          const float4 v = *reinterpret_cast<const float4*>(src + c);
-          acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+    for (int k = 0; k < 4; ++k) {
+      const int c = (threadIdx.x + k * blockDim.x) * 4;
+      if (c >= C) continue;
+      for (int i = 0; i < n; i += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (i + j < n) {
+            const int f = s_sorted[i + j];
+            const int b = f / keep, r = f - b * keep;
+            v[j] = *reinterpret_cast<const float4*>(dout + ((size_t)b * rows + r + has_cls) * C + c);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (i + j < n) { acc[k].x += v[j].x; acc[k].y += v[j].y; acc[k].z += v[j].z; acc[k].w += v[j].w; }
         }
       }
     }
@@ -419,10 +428,24 @@ __global__ void unshuffle_bwd_rowsum_kernel(const float* __restrict__ dout, cons
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), m = a;
   const float* base = dout + ((size_t)b * (L + has_cls) + has_cls + (size_t)t * G) * D + c;
   const int64_t* ids = ids_restore + (size_t)b * L + (size_t)t * G;
-  for (int s = 0; s < G; ++s) {
-    float4 v = *reinterpret_cast<const float4*>(base + (size_t)s * D);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    if (ids[s] >= keep) { m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w; }
+  // rows are added in order, fetched eight at a time (128 CTAs x 4 warps: the loop is bound by load latency, not bandwidth)
+  for (int s0 = 0; s0 < G; s0 += 8) {
+    float4 v[8];
+    bool msk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (s0 + j < G) {
+        v[j] = *reinterpret_cast<const float4*>(base + (size_t)(s0 + j) * D);
+        msk[j] = ids[s0 + j] >= keep;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (s0 + j < G) {
+        a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w;
+        if (msk[j]) { m.x += v[j].x; m.y += v[j].y; m.z += v[j].z; m.w += v[j].w; }
+      }
+    }
   }
   *reinterpret_cast<float4*>(ws_tmp + ((size_t)b * Tp + t) * D + c) = a;
   *reinterpret_cast<float4*>(ws_mt + ((size_t)b * Tp + t) * D + c) = m;
