@@ -10,21 +10,24 @@
 // dV / dK accumulate in TMEM across the sweep; dQ_m tiles go TMEM -> registers -> swizzled smem -> one asynchronous
 // cp.reduce.async.bulk (.add.f32) into an fp32 workspace that a small kernel scales and converts to bf16.
 //
-// Measured facts that shape the schedule (profiles/r1_attention_ncu.md): a tcgen05.mma with N <= 128 occupies the
-// tensor pipe for ~64 cycles whatever N is (the 128x16 A operand has to be streamed), so the 28 small MMAs of one
-// (kv tile, q tile) pair cost ~1800 cycles — the kernel is bound by the in-order MMA stream, not by FLOPs or ex2.
-// Therefore the MMA stream must never wait for the softmax threads:
-//   * the fp32 S^T / dP^T sub-tiles are double-buffered in TMEM (2 x 128 columns); the scores of sub-tile i+2 are queued
-//     behind the gradient MMAs of sub-tile i, while the threads are still working on sub-tile i+1;
+// What measurements say bounds the sweep (profiles/r2_attention_ncu.md: knock-out timings, clock64 traces of every role, ncu
+// stall samples): not the tensor pipe (removing any MMA family changes nothing; tools/microbench/mma.cu: the 16 MMAs of a sub-tile
+// occupy it ~490 clk of ~1000) and not the MUFU (moving exponentials to the FMA pipe is slower), but the LATENCY of the softmax
+// warps' dependent instruction stream and of the stage hand-offs.  Hence:
+//   * the fp32 S^T / dP^T sub-tiles have THREE stages in TMEM at head_dim 32 (3 x 128 + 96 columns; two at head_dim 64);
+//   * kAlt: the two softmax warps of a scheduler work on DIFFERENT sub-tiles (group g = warp >> 2 owns the sub-tiles of its
+//     parity, all 64 query columns, in four 16-column chunks) instead of running in phase on the two column halves of one;
+//   * the softmax statistics (-lse log2e, -delta, pre-masked by attn_delta_kernel) arrive by bulk copy with the query tile in its
+//     ring stage: per-thread global loads + an smem staging round cost every warp ~500 clk per sub-tile;
 //   * bf16 P^T / dS^T overwrite the fp32 columns their own thread has consumed (no extra columns, no cross-warp hazard);
-//   * the dS^T smem tile is double-buffered and the dQ drain of tile m is deferred by one sub-tile, so the threads
-//     never stall on the tail of the queue.
-// 512 threads in four warpgroups: warps 0-7 softmax-backward (two warps per TMEM lane quarter, 32 query columns each ->
-// two warps per scheduler hide each other's TMEM / SFU latency), warp 8 TMA producer, warp 9 MMA issuer, warps 12-15 drain
-// the dQ tiles (TMEM -> smem -> bulk reduction).  The softmax warps are the critical path of the kernel (clock64 trace:
-// they are never idle, the issuer waits for them 30-50 % of the time), so everything that is not exp / multiply / convert
-// is kept off them; draining dQ cost them ~12 % of every query tile.  setmaxnreg moves the registers of the light
-// warpgroups to the softmax warpgroups.
+//   * one arrival per WARP on the hand-off barriers;
+//   * the MMAs are issued by two warps with their own barriers: warp 9 the gradient MMAs G(i) and, right behind them in the same
+//     in-order stream, the scores S/dP(i + kNS) into the stage G(i) has just read; warp 10 the dQ MMAs (ds_ready / ds_free).  One
+//     warp issuing everything executed ~200 instructions per sub-tile as one dependent stream (~600 clk with the pipe idle).
+// 512 threads in four warpgroups: warps 0-7 softmax-backward, warp 8 TMA producer, warps 9 / 10 MMA issuers (11 only with
+// -DAB_MERGE=0), warps 12-15 drain the dQ tiles (TMEM -> smem -> bulk reduction).  setmaxnreg moves the registers of the light
+// warpgroups to the softmax warpgroups.  Per-CTA fixed cost: 4.9 us of 39 us at S = 4097 (tools/attn_overhead.py); a persistent
+// variant halved it but ran the sweep 12 % slower and was dropped (profiles/r2_attention_ncu.md).
 #include "tc_common.cuh"
 #include <type_traits>
 #include <cstdlib>
