@@ -568,7 +568,7 @@ def dominant_kernel_roofline(ops, dev, pk):
     ms_gemm = timeit(lambda: ops.gemm(GEMM_NT, a, w, M, N, K, torch.bfloat16, EPI_BIAS, bias=bias, out=o, compute=OCT_BF16))
     return {"kernel": "attn_bwd_tc_kernel<32> (+delta, dq-convert), decoder shape B8 S4097 H16 d32", "bound": "tensor",
             "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"],
-            "traffic": 306.0e6, "traffic_note": "dram read+write per launch from ncu --set full (profiles/r1_attention_ncu.md)",
+            "traffic": 305.6e6, "traffic_note": "dram read+write per launch from ncu --set full of the final kernel (profiles/r2_attention_ncu.md: 208.3 MB read + 97.3 MB written)",
             "ms_per_launch": ms, "peak_source": pk["src"],
             "sfu_bound": {"ex2_per_launch": n_exp, "achieved_gex2_s": n_exp / ms / 1e6, "peak_gex2_s": sfu_peak / 1e9,
                           "frac": n_exp / (ms * 1e-3) / sfu_peak,

@@ -73,6 +73,44 @@ def test_graph_replayed_steps_match_an_eager_torch_loop(joint):
         engine.close()
 
 
+def test_graph_replayed_steps_match_the_oracle_loop():
+    """The engine (forward, backward, clip, AdamW on the device clock; eager warm steps, capture, replays) against the loop
+    body of the reference's train_one_epoch (engine_pretrain.py:87-173) run on the CPU ORACLE: oracle forward + autograd
+    (pinned to the unmodified reference in tests/test_oracle.py), torch's clip_grad_norm_ and AdamW on CPU parameters."""
+    sd, _, _ = toy_inputs()
+    sched = dict(lr=3e-3, min_lr=1e-5, warmup_epochs=1.0, epochs=3.0)
+    eng_model = build(sd, "fp32")
+    opt = optim.FusedAdamW(optim.add_weight_decay(eng_model, 0.05), betas=(0.9, 0.95),
+                           schedule=optim.CosineSchedule(**sched, epochs_per_step=0.5))
+    engine = JointPretrainStep(eng_model, opt, mask_ratio=0.9, clip_grad=0.5, use_graph=True, warm_steps=2)
+    # CPU parameter container with the reference's names (never run: the product model has no CPU path)
+    cpu = models_mae.MaskedAutoencoderViT(**TOY.ref_kwargs(), use_flash_attn=True, precision="fp32",
+                                          norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6))
+    cpu.load_state_dict(sd, strict=True)
+    ropt = torch.optim.AdamW(optim.add_weight_decay(cpu, 0.05), lr=1.0, betas=(0.9, 0.95))
+    try:
+        for k in range(1, 6):
+            vol = O.synthetic_volume(2, 12, 64, 64, seed=110 + k, zero_pad_frames=1)
+            noise = O.synthetic_noise(2, 64, seed=120 + k)
+            res = engine(vol.to(DEV).view(1, 2, 1, 12, 64, 64), None, noise=noise.to(DEV))
+            optim.adjust_learning_rate(ropt, (k - 1) * 0.5, sched["lr"], sched["min_lr"], sched["warmup_epochs"], sched["epochs"])
+            cur = {n: p.detach() for n, p in cpu.state_dict().items()}
+            (out, grads) = O.forward_backward(TOY, cur, vol, 0.9, noise, frame_loss=True)
+            (loss, fl), _, _ = out
+            for n, p in cpu.named_parameters():
+                p.grad = grads.get(n)                              # the high-res patch embedding takes no part in a 3D step
+            norm = torch.nn.utils.clip_grad_norm_([p for p in cpu.parameters() if p.grad is not None], 0.5)
+            ropt.step()
+            got = res.check_finite()
+            assert got["loss"] == pytest.approx(float(loss.detach()), rel=2e-4), k
+            assert got["grad_norm"] == pytest.approx(float(norm), rel=1e-3), k
+            assert rel(res.frame_loss, fl.detach()) < 2e-4
+            for (name, p), (_, r) in zip(eng_model.named_parameters(), cpu.named_parameters()):
+                assert rel(p.detach(), r.detach()) < 1e-3, (k, name)
+    finally:
+        engine.close()
+
+
 def test_engine_uint8_cubes_equal_the_fp32_path():
     """A uint8 cube through ops.ingest_u8 (eager steps: fresh tensor; replayed steps: straight into the graph's static input)
     gives the same losses as feeding the CPU pipeline's fp32 volume."""

@@ -159,6 +159,11 @@ def test_module_surface_and_methods():
     assert torch.equal(m.unpatchify(p).cpu(), vol)
     rec = m.forward_encoder_decoder(vol.to(DEV))
     assert rec.shape == (2, 64, 768)
+    # models...:608-611: encoder with mask_ratio 0 (every token kept, in argsort order of the noise it draws) + decoder; the
+    # un-shuffle undoes the permutation, so the result does not depend on the noise: compare with the oracle on its own draw
+    lat_o, _, ids_o = O.forward_encoder(TOY, sd, vol, 0.0, None)
+    want_rec = O.forward_decoder(TOY, sd, lat_o, ids_o)
+    assert rel(rec, want_rec) < 1e-4
     with pytest.raises(AssertionError):
         m.forward_patch_embed(torch.zeros(1, 1, 12, 32, 32, device=DEV))     # video_vit.py:76-78
 
