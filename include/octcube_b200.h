@@ -41,7 +41,10 @@ enum { OCT_GEMM_NT = 0, OCT_GEMM_NN = 1, OCT_GEMM_TN = 2 };
  *   OCT_EPI_NONE       D = acc (+ beta·D when beta==1, fp32 D only)
  *   OCT_EPI_BIAS       D = acc + bias[n]
  *   OCT_EPI_BIAS_GELU  aux = acc + bias[n] (pre-activation, same dtype as D);  D = gelu_erf(round(aux))
- *   OCT_EPI_DGELU      D = acc · gelu_erf'(aux[m,n])          (fc2 dgrad fused with the GELU backward) */
+ *   OCT_EPI_DGELU      D = acc · gelu_erf'(aux[m,n])          (fc2 dgrad fused with the GELU backward)
+ * The bf16 tensor-core path (GELU epilogues need a bf16 D) evaluates erf-GELU through a fitted tanh form: |gelu error|
+ * <= 3e-5 + 2.5e-4 |x| (tanh.approx), |derivative error| <= 1.2e-4 + 5e-4 — below the bf16 rounding of D; the fp32
+ * entry points (oct_gelu_fwd / oct_gelu_bwd) use erfc to 1.5e-7. */
 enum { OCT_EPI_NONE = 0, OCT_EPI_BIAS = 1, OCT_EPI_BIAS_GELU = 2, OCT_EPI_DGELU = 3 };
 
 /* compute paths: OCT_F32 = fp32 CUDA-core kernels (the 1e-4 parity mode);
