@@ -154,6 +154,55 @@ __device__ __forceinline__ void softmax_tile(uint32_t tmem_s, uint32_t tmem_o, u
   l += l0 + l1;
 }
 
+// The ragged last kv tile when it holds at most 16 keys (S = 128 k + 1: the cls token of the MAE decoder / ViT sequences puts
+// ONE key into a 33rd tile): scores from an N = 16 MMA, 16 columns of softmax, one K-step of PV.  A full-width masked tile for
+// that single key cost every CTA 1/33 of its loop (tools/attn_overhead.py: S = 4097 vs 4096).
+template <int HD>
+__device__ __forceinline__ void softmax_tile_narrow(uint32_t tmem_s, uint32_t tmem_o, uint64_t* o_done, int j, int valid,
+                                                    float scale_log2e, float& m, float& l) {
+  uint32_t sr[16];
+  tc::tmem_ld_x16(tmem_s, sr);
+  tc::tmem_ld_wait();
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i >= valid) sr[i] = 0xff800000u;  // -inf
+    mx = fmaxf(mx, __uint_as_float(sr[i]));
+  }
+  const float m_tile = mx * scale_log2e;
+  const bool need = m_tile > m + kRescaleThreshold;  // always true on the first tile (m = -inf)
+  if (__any_sync(0xffffffffu, need)) {
+    const float m_new = need ? m_tile : m;
+    if (j > 0) {
+      const float factor = need ? tc::fast_exp2(m - m_new) : 1.f;
+      tc::mbar_wait(o_done, (j - 1) & 1);  // O += P(j-1) V_{j-1} has landed
+      tc::tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD / 16; ++c) {
+        uint32_t o[16];
+        tc::tmem_ld_x16(tmem_o + c * 16, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+        tc::tmem_st_x16(tmem_o + c * 16, o);
+      }
+      l *= factor;
+    }
+    m = m_new;
+  }
+  uint32_t pk[8];
+  float ls = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // masked columns hold -inf -> exactly 0
+    const float p0 = tc::fast_exp2(fmaf(__uint_as_float(sr[2 * i]), scale_log2e, -m));
+    const float p1 = tc::fast_exp2(fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2e, -m));
+    ls += p0 + p1;
+    pk[i] = pack_bf16x2(p0, p1);
+  }
+  tc::tmem_st_x8(tmem_s, pk);
+  l += ls;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                     const AtParams p) {
@@ -173,8 +222,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   // which the warpgroup arrives on after consuming s_full(n) — no barrier can run two phases ahead of its waiter
   uint64_t* s_full = kv_empty + AT_KV_STAGES;  // [AT_SBUFS]
   uint64_t* p_full = s_full + AT_SBUFS;        // [AT_SBUFS]
-  uint64_t* o_done = p_full + AT_SBUFS;        // [AT_QT]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + AT_QT);
+  uint64_t* o_done = p_full + AT_SBUFS;        // [AT_QT] every PV of Q tile t (waited on only when O must be rescaled)
+  uint64_t* o_final = o_done + AT_QT;          // [AT_QT] the LAST PV of Q tile t (single phase: the epilogue's wait)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + AT_QT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (AT_QT * AT_BM), h = blockIdx.y, b = blockIdx.z;
@@ -182,6 +232,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   // The last CTA of a (batch, head) may own a single live Q tile (S = 4097: one query row in the 17th CTA); then score
   // tile n is simply kv tile n of Q tile 0 and warpgroup 1 idles, instead of sweeping the keys for 128 rows that do not exist.
   const int qsh = (q0 + AT_BM < p.S) ? 1 : 0;  // log2(number of live Q tiles): tile n -> (t = n & qsh, j = n >> qsh)
+  const bool narrow_last = (p.S - (n_kv - 1) * AT_BN) <= 16;  // the last kv tile holds <= 16 keys: N = 16 scores, one PV K-step
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
@@ -191,7 +242,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       tc::mbar_init(&s_full[i], 1);
       tc::mbar_init(&p_full[i], 128);
     }
-    for (int t = 0; t < AT_QT; ++t) tc::mbar_init(&o_done[t], 1);
+    for (int t = 0; t < AT_QT; ++t) { tc::mbar_init(&o_done[t], 1); tc::mbar_init(&o_final[t], 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
@@ -223,17 +274,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     // thread), which made this warp — not the SFU — the bottleneck of the kernel (93 % busy, profiles/r1_attention_ncu.md).
     {
       constexpr uint32_t idesc_qk = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, AT_BN);
+      constexpr uint32_t idesc_qk16 = tc::make_idesc(tc::kFmtBF16, false, false, AT_BM, 16);
       constexpr uint32_t idesc_pv = tc::make_idesc(tc::kFmtBF16, false, true, AT_BM, HD);
       auto issue_qk = [&](int n) {  // score tile n: Q tile n & qsh against K_(n >> qsh)
         const int t = n & qsh, stage = (n >> qsh) % AT_KV_STAGES;
         const uint32_t q_addr = tc::smem_u32(sQ + t * C::kTileBytes);
         const uint32_t k_addr = tc::smem_u32(sK + stage * C::kTileBytes);
         const uint32_t d_addr = tmem_base + C::kColS + (n % AT_SBUFS) * 128;
+        const uint32_t idesc = (narrow_last && (n >> qsh) == n_kv - 1) ? idesc_qk16 : idesc_qk;
 #pragma unroll
         for (int k = 0; k < ((AT_KNOCK & 16) ? 0 : HD / 16); ++k) {
           const uint64_t da = tc::make_smem_desc(q_addr + k * 32, 16, C::kSBO, C::kSwz);
           const uint64_t db = tc::make_smem_desc(k_addr + k * 32, 16, C::kSBO, C::kSwz);
-          tc::mma_ss(d_addr, da, db, idesc_qk, k != 0);
+          tc::mma_ss(d_addr, da, db, idesc, k != 0);
         }
         tc::mma_commit(&s_full[n % AT_SBUFS]);
       };
@@ -241,13 +294,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
         const int t = n & qsh, j = n >> qsh, stage = j % AT_KV_STAGES;
         const uint32_t v_addr = tc::smem_u32(sV + stage * C::kTileBytes);
         const uint32_t p_addr = tmem_base + C::kColS + (n % AT_SBUFS) * 128;
+        if (narrow_last && j == n_kv - 1) {  // narrow tile: P holds 16 keys, one K-step
+          const uint64_t db = tc::make_smem_desc(v_addr, C::kTileBytes, C::kSBO, C::kSwz);
+          tc::mma_ts(tmem_base + C::kColO + t * HD, p_addr, db, idesc_pv, j != 0);
+        } else {
 #pragma unroll
-        for (int k = 0; k < ((AT_KNOCK & 8) ? 0 : AT_BN / 16); ++k) {
-          // V as an MN-major B operand: 16 kv rows per step; one MN chunk (= HD elements) so LBO is unused
-          const uint64_t db = tc::make_smem_desc(v_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
-          tc::mma_ts(tmem_base + C::kColO + t * HD, p_addr + k * 8, db, idesc_pv, (j | k) != 0);
+          for (int k = 0; k < ((AT_KNOCK & 8) ? 0 : AT_BN / 16); ++k) {
+            // V as an MN-major B operand: 16 kv rows per step; one MN chunk (= HD elements) so LBO is unused
+            const uint64_t db = tc::make_smem_desc(v_addr + k * 16 * C::kRowBytes, C::kTileBytes, C::kSBO, C::kSwz);
+            tc::mma_ts(tmem_base + C::kColO + t * HD, p_addr + k * 8, db, idesc_pv, (j | k) != 0);
+          }
         }
         tc::mma_commit(&o_done[t]);
+        if (j == n_kv - 1) tc::mma_commit(&o_final[t]);
       };
       auto wait_kv = [&](int j) {
         tc::mbar_wait(&kv_full[j % AT_KV_STAGES], (j / AT_KV_STAGES) & 1);
@@ -298,14 +357,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       const uint32_t tmem_s = lane_addr + C::kColS + buf * 128;
       if (valid >= AT_BN)
         softmax_tile<HD, false>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
+      else if (narrow_last)
+        softmax_tile_narrow<HD>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       else
         softmax_tile<HD, true>(tmem_s, tmem_o, &o_done[t], j, valid, p.scale_log2e, m, l);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&p_full[buf]);
     }
-    // epilogue: O / l -> bf16, lse
-    tc::mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    // epilogue: O / l -> bf16, lse.  The last PV of this Q tile arrives on its own single-phase barrier: a parity wait on o_done
+    // is only unambiguous while that barrier is at most one phase behind the phase waited for, and nothing guarantees that
+    // PV(n_kv - 2) has completed when the last tile's softmax is done (it normally has — the softmax takes longer than a PV round
+    // trip — but a 16-key ragged-tile experiment did not, and read O two PVs early).
+    tc::mbar_wait(&o_final[t], 0);
     tc::tcgen05_fence_after();
     const int qi = q0 + t * AT_BM + row;
     const float inv = 1.f / l;
