@@ -237,6 +237,9 @@ int oct_resize_trilinear_u8(const uint8_t* src, float* dst, const int* box, int6
 
 /* ---- fp32 -> bf16 shadow copy of parameters (the autocast weight cast, done once per step) ------------------- */
 int oct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, oct_stream_t stream);
+/* every shadow in one launch: `table` = device int64 [n_chunks][3] = {src pointer (16-byte aligned fp32), dst pointer (8-byte
+ * aligned bf16), element count <= 16384}; chunks never cross a tensor */
+int oct_cast_f32_to_bf16_multi(const int64_t* table, int64_t n_chunks, oct_stream_t stream);
 
 /* ---- fused multi-tensor AdamW (replaces torch.optim._multi_tensor.AdamW, main_pretrain...:451-455, the GradScaler unscale
  * before it and the next forward's bf16 weight casts) -----------------------------------------------------------------

@@ -60,6 +60,7 @@ SIGNATURES = {
     "oct_fg_bbox_u8": (I, [P, P, L, L, L, L, P]),
     "oct_resize_trilinear_u8": (I, [P, P, P, L, L, L, L, L, L, L, I, I, F, P]),
     "oct_cast_f32_to_bf16": (I, [P, P, L, P]),
+    "oct_cast_f32_to_bf16_multi": (I, [P, L, P]),
     "oct_adamw_step": (I, [P, L, F, F, F, F, F, L, F, P, P]),
     "oct_adamw_clock_advance": (I, [P, F, F, F, F, F, F, F, P]),
     "oct_adamw_step_clocked": (I, [P, L, P, F, F, F, F, F, F, P, P]),

@@ -40,6 +40,7 @@ class _Shadows:
 
     def __init__(self):
         self._m = {}
+        self._table = None   # (key, device chunk table, chunks) of the multi-tensor cast over all registered shadows
 
     def get(self, p: torch.Tensor) -> torch.Tensor:
         ent = self._m.get(id(p))
@@ -55,8 +56,29 @@ class _Shadows:
         return ent["buf"]
 
     def begin_step(self):
-        for ent in self._m.values():
+        """Start of a forward pass.  Every shadow that get() would re-cast in this pass (master changed, or a pass that is
+        being captured) is refreshed HERE by one multi-tensor launch — ~200 per-parameter launches per step otherwise —
+        provided that is all of them (the usual case); anything else is left to get()."""
+        ents = list(self._m.values())
+        for ent in ents:
             ent["fresh"] = False
+        if not ents:
+            return
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not all(ent["ptr"] == ent["p"].data_ptr() for ent in ents):
+            return                           # a parameter was re-allocated: get() re-registers it
+        key = tuple((ent["ptr"], ent["buf"].data_ptr()) for ent in ents)
+        if self._table is None or self._table[0] != key:
+            if capturing:
+                return                       # the table upload is a host-to-device copy: never inside a capture
+            tab, n = ops.cast_table([(ent["p"].detach(), ent["buf"]) for ent in ents])
+            self._table = (key, tab, n)
+        if not all(capturing or ent["ver"] != ent["p"]._version for ent in ents):
+            return                           # some (or all) shadows are current: get() refreshes the others
+        ops.cast_bf16_multi(self._table[1], self._table[2])
+        for ent in ents:
+            ent["ver"] = ent["p"]._version
+            ent["fresh"] = True
 
     def buffer_of(self, p):
         ent = self._m.get(id(p))

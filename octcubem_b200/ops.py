@@ -406,6 +406,28 @@ def cast_bf16(src_f32, dst_bf16=None):
     return dst_bf16
 
 
+CAST_CHUNK = 16384
+
+
+def cast_table(pairs):
+    """Device chunk table for cast_bf16_multi: `pairs` = [(fp32 source, bf16 destination)], same numel, contiguous."""
+    rows = []
+    for src, dst in pairs:
+        _chk(src, dst)
+        assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+        assert src.is_contiguous() and dst.is_contiguous() and src.data_ptr() % 16 == 0 and dst.data_ptr() % 8 == 0
+        n = src.numel()
+        for off in range(0, n, CAST_CHUNK):
+            rows.append((src.data_ptr() + 4 * off, dst.data_ptr() + 2 * off, min(CAST_CHUNK, n - off)))
+    dev = pairs[0][0].device
+    return torch.tensor(rows, dtype=torch.int64).to(dev), len(rows)
+
+
+def cast_bf16_multi(table, n_chunks):
+    """fp32 -> bf16 of every (source, destination) pair of a cast_table in one launch."""
+    _call("oct_cast_f32_to_bf16_multi", _p(table), n_chunks, _stream())
+
+
 def _wgrad_into_sinks(dy2, x2, w_sink, b_sink):
     """Weight + bias gradient of one nn.Linear, produced in the reducer's buckets when they are registered (see _sink)."""
     dw, beta_w, give_w = _sink(*w_sink)

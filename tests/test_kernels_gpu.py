@@ -552,6 +552,20 @@ def test_patch_embed_tc(B, T, HW, E, u):
     assert rel(out, want) < 2e-3  # tf32 operands (10-bit mantissa), fp32 accumulate
 
 
+def test_cast_bf16_multi_matches_the_per_tensor_cast():
+    """oct_cast_f32_to_bf16_multi (all weight shadows in one launch, chunk table) against the per-tensor cast: bit-equal,
+    including tails that are not multiples of 4 and tensors longer than one chunk."""
+    g = torch.Generator().manual_seed(5)
+    srcs = [torch.randn(n, generator=g).to(DEV) for n in (7, 16384, 16385, 40000, 1024 * 1024 + 3, 64)]
+    dsts = [torch.empty(t.numel(), dtype=torch.bfloat16, device=DEV) for t in srcs]
+    table, n = ops.cast_table(list(zip(srcs, dsts)))
+    assert n == sum((t.numel() + ops.CAST_CHUNK - 1) // ops.CAST_CHUNK for t in srcs)
+    ops.cast_bf16_multi(table, n)
+    for s_, d_ in zip(srcs, dsts):
+        assert torch.equal(d_, ops.cast_bf16(s_))
+        assert torch.equal(d_, s_.bfloat16())
+
+
 def test_gemm_tc_from_fresh_thread():
     """A thread without a bound CUDA context (a new autograd worker) must be able to call the TMA-based GEMM."""
     import threading
